@@ -1,0 +1,944 @@
+// api.cu — the C ABI (include/norma_b200.h): context, weight loading, encoder orchestration, decode loop.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+static thread_local std::string g_err;
+int decoder_logits_rows(nb200_ctx *ctx, int n);
+
+int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_err = buf;
+    return code;
+}
+
+KernelScope::KernelScope(nb200_ctx *c, int k) : ctx(c), cls(k) {
+    ctx->launches++;
+    ctx->prof_launches[cls]++;
+    if (ctx->profiling) {
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, ctx->stream);
+    }
+}
+KernelScope::~KernelScope() {
+    if (a) {
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof_recs.push_back({cls, a, b});
+    }
+}
+
+namespace {
+
+int dev_alloc(nb200_ctx *ctx, size_t bytes, void **out, bool zero = false) {
+    if (bytes == 0) bytes = 16;
+    CUDA_TRY(ctx, cudaMalloc(out, bytes));
+    ctx->allocs.push_back(*out);
+    ctx->device_bytes += bytes;
+    if (zero) CUDA_TRY(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->stream));
+    return NB200_OK;
+}
+template <typename T>
+int dev_alloc_t(nb200_ctx *ctx, size_t n, T **out, bool zero = false) { return dev_alloc(ctx, n * sizeof(T), (void **)out, zero); }
+
+int set_device(nb200_ctx *ctx) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->ordinal));
+    return NB200_OK;
+}
+
+int ensure_pinned(nb200_ctx *ctx, size_t bytes) {
+    if (ctx->host_pinned_bytes >= bytes) return NB200_OK;
+    if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+    ctx->host_pinned = nullptr;
+    ctx->host_pinned_bytes = 0;
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->host_pinned, bytes));
+    ctx->host_pinned_bytes = bytes;
+    return NB200_OK;
+}
+
+int upload_f32(nb200_ctx *ctx, const std::vector<float> &v, float **out) {
+    NB_TRY(dev_alloc_t(ctx, v.size(), out));
+    CUDA_TRY(ctx, cudaMemcpyAsync(*out, v.data(), v.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+// upload in the compute dtype (f32 -> bf16 conversion on the device)
+int upload_compute(nb200_ctx *ctx, const std::vector<float> &v, void **out) {
+    if (ctx->compute == NB200_F32) return upload_f32(ctx, v, (float **)out);
+    float *tmp = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&tmp, v.size() * 4));
+    cudaError_t e = cudaMemcpyAsync(tmp, v.data(), v.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    int st = NB200_OK;
+    if (e == cudaSuccess) {
+        st = dev_alloc(ctx, v.size() * 2, out);
+        if (st == NB200_OK) st = launch_f32_to_bf16(ctx, tmp, (bf16 *)*out, v.size());
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "weight upload failed: %s", cudaGetErrorString(e));
+    return st;
+}
+
+const HostTensor *find(nb200_ctx *ctx, const std::string &name) {
+    auto it = ctx->host_tensors.find(name);
+    return it == ctx->host_tensors.end() ? nullptr : &it->second;
+}
+
+int need(nb200_ctx *ctx, const std::string &name, size_t numel, const HostTensor **out) {
+    const HostTensor *t = find(ctx, name);
+    if (!t) return nb200_fail(ctx, NB200_NOT_LOADED, "tensor '%s' was not loaded", name.c_str());
+    if (t->data.size() != numel)
+        return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "tensor '%s' has %zu elements, expected %zu", name.c_str(), t->data.size(), numel);
+    *out = t;
+    return NB200_OK;
+}
+
+int up_vec(nb200_ctx *ctx, const std::string &name, size_t n, float **out) {
+    const HostTensor *t;
+    NB_TRY(need(ctx, name, n, &t));
+    return upload_f32(ctx, t->data, out);
+}
+int up_mat(nb200_ctx *ctx, const std::string &name, size_t n, void **out) {
+    const HostTensor *t;
+    NB_TRY(need(ctx, name, n, &t));
+    return upload_compute(ctx, t->data, out);
+}
+
+// concatenated [q | k | v] weight and bias ([3d][d], [3d] with zeros for the bias-less k_proj)
+int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b) {
+    const HostTensor *q, *k, *v, *bq, *bv;
+    NB_TRY(need(ctx, p + "q_proj.weight", (size_t)d * d, &q));
+    NB_TRY(need(ctx, p + "k_proj.weight", (size_t)d * d, &k));
+    NB_TRY(need(ctx, p + "v_proj.weight", (size_t)d * d, &v));
+    NB_TRY(need(ctx, p + "q_proj.bias", d, &bq));
+    NB_TRY(need(ctx, p + "v_proj.bias", d, &bv));
+    std::vector<float> W((size_t)3 * d * d), B(3 * d, 0.f);
+    memcpy(W.data(), q->data.data(), (size_t)d * d * 4);
+    memcpy(W.data() + (size_t)d * d, k->data.data(), (size_t)d * d * 4);
+    memcpy(W.data() + (size_t)2 * d * d, v->data.data(), (size_t)d * d * 4);
+    memcpy(B.data(), bq->data.data(), d * 4);
+    memcpy(B.data() + 2 * d, bv->data.data(), d * 4);
+    NB_TRY(upload_compute(ctx, W, w));
+    return upload_f32(ctx, B, b);
+}
+
+// conv weight [co][ci][3] -> [co][k*ci_n + ci] (tap-major) so a GEMM row is 3 consecutive time-major input rows
+int up_conv(nb200_ctx *ctx, const std::string &name, int co, int ci, void **out) {
+    const HostTensor *t;
+    NB_TRY(need(ctx, name, (size_t)co * ci * 3, &t));
+    std::vector<float> W((size_t)co * ci * 3);
+    for (int o = 0; o < co; ++o)
+        for (int i = 0; i < ci; ++i)
+            for (int k = 0; k < 3; ++k) W[((size_t)o * 3 + k) * ci + i] = t->data[((size_t)o * ci + i) * 3 + k];
+    return upload_compute(ctx, W, out);
+}
+
+float bf16_bits_to_float(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+float f16_bits_to_float(uint16_t h) {
+    uint32_t sign = (h >> 15) & 1, exp = (h >> 10) & 0x1f, man = h & 0x3ff, u;
+    if (exp == 0) {
+        if (man == 0) u = sign << 31;
+        else {
+            int e = -1;
+            do { man <<= 1; ++e; } while (!(man & 0x400));
+            u = (sign << 31) | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ff) << 13);
+        }
+    } else if (exp == 31) u = (sign << 31) | 0x7f800000u | (man << 13);
+    else u = (sign << 31) | ((exp - 15 + 127) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+int alloc_decoder(nb200_ctx *ctx) {
+    const nb200_config &c = ctx->cfg;
+    const size_t es = dtype_size(ctx->compute), B = c.max_batch, d = c.d_model;
+    NB_TRY(dev_alloc(ctx, (size_t)c.decoder_layers * B * c.max_source_positions * 2 * d * es, &ctx->cross_kv));
+    NB_TRY(dev_alloc(ctx, (size_t)c.decoder_layers * B * c.max_target_positions * 2 * d * es, &ctx->self_kv, true));
+    NB_TRY(dev_alloc_t(ctx, B * d, &ctx->dx));
+    NB_TRY(dev_alloc_t(ctx, B * d, &ctx->dh));
+    NB_TRY(dev_alloc_t(ctx, B * 3 * d, &ctx->dqkv));
+    NB_TRY(dev_alloc_t(ctx, B * d, &ctx->dattn));
+    NB_TRY(dev_alloc_t(ctx, B * 4 * d, &ctx->dff));
+    NB_TRY(dev_alloc_t(ctx, B * d, &ctx->dq));
+    NB_TRY(dev_alloc_t(ctx, std::max<size_t>(B, c.max_target_positions) * d, &ctx->dhid));
+    NB_TRY(dev_alloc_t(ctx, B * c.vocab_size, &ctx->logits));
+    NB_TRY(dev_alloc_t(ctx, B * c.max_target_positions, &ctx->d_tokens, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_len, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_last_ts, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_done, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_nsampled, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_sumlp, true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->d_nospeech, true));
+    NB_TRY(dev_alloc_t(ctx, (size_t)c.vocab_size, &ctx->suppress, true));
+    return NB200_OK;
+}
+
+int upload_suppress(nb200_ctx *ctx) {
+    if (!ctx->suppress) return NB200_OK;
+    std::vector<float> m(ctx->cfg.vocab_size, 0.f);
+    for (uint32_t t : ctx->suppress_ids)
+        if (t < (uint32_t)ctx->cfg.vocab_size) m[t] = -INFINITY;
+    if (ctx->has_tokens && ctx->tok.no_timestamps < (uint32_t)ctx->cfg.vocab_size) m[ctx->tok.no_timestamps] = -INFINITY;  // monolingual.rs:388
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->suppress, m.data(), m.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int stage_pcm(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens) {
+    if (!pcm || n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "stage_pcm: n_windows=%zu (max_batch %d)", n_windows, ctx->cfg.max_batch);
+    std::vector<int> l(n_windows);
+    for (size_t w = 0; w < n_windows; ++w) {
+        size_t n = lens ? lens[w] : stride;
+        if (n > (size_t)N_SAMPLES) return nb200_fail(ctx, NB200_INVALID_ARG, "window %zu has %zu samples (> %d)", w, n, N_SAMPLES);
+        l[w] = (int)n;
+        if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm + w * N_SAMPLES, pcm + w * stride, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm_len, l.data(), n_windows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `l` and possibly pageable `pcm` are consumed
+    return NB200_OK;
+}
+
+int check_ready(nb200_ctx *ctx, bool need_weights, bool need_filters) {
+    if (!ctx) return NB200_INVALID_ARG;
+    NB_TRY(set_device(ctx));
+    if (need_weights && !ctx->finalized) return nb200_fail(ctx, NB200_NOT_LOADED, "weights not finalized (call nb200_finalize_weights)");
+    if (need_filters && !ctx->has_filters) return nb200_fail(ctx, NB200_NOT_LOADED, "mel filters not set (call nb200_set_mel_filters)");
+    return NB200_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// encoder: candle `AudioEncoder::forward` on windows [0, B)
+// ---------------------------------------------------------------------------------------------------------
+static int g_attn_impl = -1;  // -1 unset, 0 simt, 1 tcgen05
+
+int encoder_run(nb200_ctx *ctx, int B) {
+    const nb200_config &c = ctx->cfg;
+    const int d = c.d_model, T = c.max_source_positions, n_mel = c.num_mel_bins, H = c.encoder_attention_heads;
+    const bool bf = ctx->compute == NB200_BF16;
+    const int M = B * T;
+    const float qk_scale = powf((float)HEAD_DIM, -0.25f);
+    if (g_attn_impl < 0) {
+        const char *e = getenv("NB200_ATTN");
+        g_attn_impl = (e && !strcmp(e, "tc")) ? 1 : 0;  // default SIMT until the tcgen05 kernel is validated
+    }
+    auto gemm = [&](const void *A, const void *W, const GemmShape &s, const Epilogue &e) {
+        return bf ? launch_gemm_bf16(ctx, (const bf16 *)A, (const bf16 *)W, s, e) : launch_gemm_f32(ctx, (const float *)A, (const float *)W, s, e);
+    };
+    const size_t es = dtype_size(ctx->compute);
+    // conv1 (k3, s1, p1) + GELU as a GEMM over overlapping rows of the time-major mel buffer
+    {
+        GemmShape s{N_FRAMES, B, d, 3 * n_mel, n_mel, (long long)(N_FRAMES + 2) * n_mel};
+        Epilogue e{};
+        e.bias = ctx->conv1_b; e.act = 1;
+        e.out = (char *)ctx->y1 + (size_t)d * es;  // row 0 of every window is the zero pad
+        e.ldo = d; e.out_bs = (long long)(N_FRAMES + 1) * d; e.out_bf16 = bf;
+        NB_TRY(gemm(ctx->melT, ctx->conv1_w, s, e));
+    }
+    // conv2 (k3, s2, p1) + GELU + sinusoidal positions -> residual stream x [B*1500][d] f32
+    {
+        GemmShape s{T, B, d, 3 * d, 2 * d, (long long)(N_FRAMES + 1) * d};
+        Epilogue e{};
+        e.bias = ctx->conv2_b; e.act = 1;
+        e.residual = ctx->pos; e.ldr = d; e.res_bs = 0;
+        e.out = ctx->x; e.ldo = d; e.out_bs = (long long)T * d; e.out_bf16 = 0;
+        NB_TRY(gemm(ctx->y1, ctx->conv2_w, s, e));
+    }
+    for (int l = 0; l < c.encoder_layers; ++l) {
+        const EncLayer &w = ctx->enc[l];
+        NB_TRY(launch_layernorm(ctx, ctx->x, w.ln1g, w.ln1b, M, d, ctx->h, bf, nullptr));
+        {
+            GemmShape s{M, 1, 3 * d, d, d, (long long)M * d};
+            Epilogue e{};
+            e.bias = w.bqkv; e.scale = qk_scale; e.n_scale = 2 * d;  // q and k each scaled by hd^-0.25
+            e.out = ctx->qkv; e.ldo = 3 * d; e.out_bf16 = bf;
+            NB_TRY(gemm(ctx->h, w.wqkv, s, e));
+        }
+        if (bf && g_attn_impl == 1) NB_TRY(launch_attention_tc(ctx, (const bf16 *)ctx->qkv, (bf16 *)ctx->attn, B, T, H));
+        else NB_TRY(launch_attention_simt(ctx, ctx->qkv, ctx->attn, B, T, H, bf));
+        {
+            GemmShape s{M, 1, d, d, d, (long long)M * d};
+            Epilogue e{};
+            e.bias = w.bo; e.residual = ctx->x; e.ldr = d;
+            e.out = ctx->x; e.ldo = d; e.out_bf16 = 0;
+            NB_TRY(gemm(ctx->attn, w.wo, s, e));
+        }
+        NB_TRY(launch_layernorm(ctx, ctx->x, w.ln2g, w.ln2b, M, d, ctx->h, bf, nullptr));
+        {
+            GemmShape s{M, 1, 4 * d, d, d, (long long)M * d};
+            Epilogue e{};
+            e.bias = w.b1; e.act = 1;
+            e.out = ctx->ff; e.ldo = 4 * d; e.out_bf16 = bf;
+            NB_TRY(gemm(ctx->h, w.w1, s, e));
+        }
+        {
+            GemmShape s{M, 1, d, 4 * d, 4 * d, (long long)M * 4 * d};
+            Epilogue e{};
+            e.bias = w.b2; e.residual = ctx->x; e.ldr = d;
+            e.out = ctx->x; e.ldo = d; e.out_bf16 = 0;
+            NB_TRY(gemm(ctx->ff, w.w2, s, e));
+        }
+    }
+    // ln_post -> audio features (f32) and, in bf16 mode, the bf16 copy the cross-K/V GEMM consumes
+    if (bf) NB_TRY(launch_layernorm(ctx, ctx->x, ctx->lnpost_g, ctx->lnpost_b, M, d, ctx->enc_out_c, 1, ctx->enc_out));
+    else NB_TRY(launch_layernorm(ctx, ctx->x, ctx->lnpost_g, ctx->lnpost_b, M, d, ctx->enc_out, 0, nullptr));
+    ctx->n_resident = B;
+    ctx->cross_valid = false;
+    return NB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nb200_device_count(int *out) {
+    if (!out) return nb200_fail(nullptr, NB200_INVALID_ARG, "device_count: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out = 0;
+        return nb200_fail(nullptr, NB200_CUDA_ERROR, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *out = n;
+    return NB200_OK;
+}
+
+const char *nb200_last_error(nb200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb200_ctx **out) {
+    if (!cfg || !out) return nb200_fail(nullptr, NB200_INVALID_ARG, "create: NULL argument");
+    *out = nullptr;
+    if (compute != NB200_BF16 && compute != NB200_F32) return nb200_fail(nullptr, NB200_INVALID_ARG, "create: compute dtype must be BF16 or F32");
+    const nb200_config &c = *cfg;
+    if (c.num_mel_bins != 80 && c.num_mel_bins != 128)
+        return nb200_fail(nullptr, NB200_UNSUPPORTED_SHAPE, "Unexpected number of mel bins (num_mel_bins), got: %d", c.num_mel_bins);  // whisper::Error::MelBins
+    if (c.d_model % 128 != 0 || c.d_model > 1280 || c.d_model < 128 || c.encoder_attention_heads * HEAD_DIM != c.d_model ||
+        c.decoder_attention_heads * HEAD_DIM != c.d_model)
+        return nb200_fail(nullptr, NB200_UNSUPPORTED_SHAPE, "d_model=%d heads=%d/%d: need d_model %% 128 == 0, <= 1280, head_dim 64", c.d_model,
+                          c.encoder_attention_heads, c.decoder_attention_heads);
+    if (c.max_source_positions != 1500 || c.max_target_positions < 8 || c.max_target_positions > 448 || c.max_batch < 1 || c.encoder_layers < 1 ||
+        c.decoder_layers < 0 || c.vocab_size < 1)
+        return nb200_fail(nullptr, NB200_UNSUPPORTED_SHAPE, "unsupported config (max_source_positions must be 1500, max_target_positions in [8, 448])");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return nb200_fail(nullptr, NB200_CUDA_ERROR, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    if (ordinal < 0 || ordinal >= ndev) return nb200_fail(nullptr, NB200_INVALID_ARG, "create: ordinal %d out of range (%d devices)", ordinal, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, ordinal);
+    if (e != cudaSuccess) return nb200_fail(nullptr, NB200_CUDA_ERROR, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return nb200_fail(nullptr, NB200_ARCH_MISMATCH, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", ordinal, prop.major,
+                          prop.minor);
+    nb200_ctx *ctx = new nb200_ctx();
+    ctx->ordinal = ordinal;
+    ctx->cfg = c;
+    ctx->compute = compute;
+    ctx->sm_count = prop.multiProcessorCount;
+    int st = [&]() -> int {
+        NB_TRY(set_device(ctx));
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_start));
+        CUDA_TRY(ctx, cudaEventCreate(&ctx->ev_stop));
+        const size_t B = c.max_batch, d = c.d_model, T = c.max_source_positions, nm = c.num_mel_bins, es = dtype_size(compute);
+        const size_t M = B * T;
+        NB_TRY(dev_alloc_t(ctx, (size_t)nm * 16, &ctx->filt_vals, true));
+        NB_TRY(dev_alloc_t(ctx, nm, &ctx->filt_start, true));
+        NB_TRY(dev_alloc_t(ctx, nm, &ctx->filt_len, true));
+        NB_TRY(dev_alloc_t(ctx, 1280, &ctx->mel_tables, true));
+        NB_TRY(dev_alloc_t(ctx, B * N_SAMPLES, &ctx->pcm, true));
+        NB_TRY(dev_alloc_t(ctx, B, &ctx->pcm_len, true));
+        NB_TRY(dev_alloc_t(ctx, B * nm * N_FRAMES, &ctx->logmel));
+        NB_TRY(dev_alloc_t(ctx, B, &ctx->mel_max, true));
+        NB_TRY(dev_alloc_t(ctx, B * nm * N_FRAMES, &ctx->mel_norm));
+        NB_TRY(dev_alloc(ctx, B * (N_FRAMES + 2) * nm * es, &ctx->melT, true));
+        NB_TRY(dev_alloc(ctx, B * (N_FRAMES + 1) * d * es, &ctx->y1, true));
+        NB_TRY(dev_alloc_t(ctx, M * d, &ctx->x));
+        NB_TRY(dev_alloc(ctx, M * d * es, &ctx->h));
+        NB_TRY(dev_alloc(ctx, M * 3 * d * es, &ctx->qkv));
+        NB_TRY(dev_alloc(ctx, M * d * es, &ctx->attn));
+        NB_TRY(dev_alloc(ctx, M * 4 * d * es, &ctx->ff));
+        NB_TRY(dev_alloc_t(ctx, M * d, &ctx->enc_out));
+        if (compute == NB200_BF16) NB_TRY(dev_alloc(ctx, M * d * 2, &ctx->enc_out_c));
+        else ctx->enc_out_c = ctx->enc_out;
+        ctx->flush_bytes = 256ull << 20;
+        NB_TRY(dev_alloc(ctx, ctx->flush_bytes, &ctx->flush_buf));
+        NB_TRY(mel_setup_tables(ctx));
+        NB_TRY(simt_init(ctx));
+        NB_TRY(gemm_tc_init(ctx));
+        NB_TRY(attn_tc_init(ctx));
+        NB_TRY(decoder_init(ctx));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    }();
+    if (st != NB200_OK) {
+        g_err = ctx->err;
+        nb200_destroy(ctx);
+        return st;
+    }
+    *out = ctx;
+    return NB200_OK;
+}
+
+void nb200_destroy(nb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->ordinal);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->allocs) cudaFree(p);
+    for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+    if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+    if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int nb200_query(nb200_ctx *ctx, nb200_query_key key, int64_t *out) {
+    if (!ctx || !out) return nb200_fail(ctx, NB200_INVALID_ARG, "query: NULL argument");
+    switch (key) {
+        case NB200_Q_N_FRAMES: *out = N_FRAMES; break;
+        case NB200_Q_ENC_LEN: *out = ctx->cfg.max_source_positions; break;
+        case NB200_Q_D_MODEL: *out = ctx->cfg.d_model; break;
+        case NB200_Q_VOCAB: *out = ctx->cfg.vocab_size; break;
+        case NB200_Q_MAX_BATCH: *out = ctx->cfg.max_batch; break;
+        case NB200_Q_KERNEL_LAUNCHES: *out = ctx->launches; break;
+        case NB200_Q_DEVICE_BYTES: *out = (int64_t)ctx->device_bytes; break;
+        case NB200_Q_COMPUTE_DTYPE: *out = ctx->compute; break;
+        default: return nb200_fail(ctx, NB200_INVALID_ARG, "query: unknown key %d", (int)key);
+    }
+    return NB200_OK;
+}
+
+int nb200_sync(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_load_tensor(nb200_ctx *ctx, const char *hf_name, const void *host, nb200_dtype dtype, const int64_t *shape, int rank) {
+    if (!ctx || !hf_name || !host || !shape || rank < 1 || rank > 4) return nb200_fail(ctx, NB200_INVALID_ARG, "load_tensor: bad argument");
+    if (ctx->finalized) return nb200_fail(ctx, NB200_INVALID_ARG, "load_tensor: weights already finalized");
+    size_t n = 1;
+    for (int i = 0; i < rank; ++i) {
+        if (shape[i] <= 0) return nb200_fail(ctx, NB200_INVALID_ARG, "load_tensor: non-positive dimension");
+        n *= (size_t)shape[i];
+    }
+    if (!strcmp(hf_name, "model.encoder.embed_positions.weight")) return NB200_OK;  // candle recomputes sinusoids
+    HostTensor t;
+    t.shape.assign(shape, shape + rank);
+    t.data.resize(n);
+    switch (dtype) {
+        case NB200_F32: memcpy(t.data.data(), host, n * 4); break;
+        case NB200_BF16: for (size_t i = 0; i < n; ++i) t.data[i] = bf16_bits_to_float(((const uint16_t *)host)[i]); break;
+        case NB200_F16: for (size_t i = 0; i < n; ++i) t.data[i] = f16_bits_to_float(((const uint16_t *)host)[i]); break;
+        case NB200_F64: for (size_t i = 0; i < n; ++i) t.data[i] = (float)((const double *)host)[i]; break;
+        default: return nb200_fail(ctx, NB200_INVALID_ARG, "load_tensor: unsupported dtype %d for '%s'", (int)dtype, hf_name);
+    }
+    ctx->host_tensors[hf_name] = std::move(t);
+    return NB200_OK;
+}
+
+int nb200_finalize_weights(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (ctx->finalized) return nb200_fail(ctx, NB200_INVALID_ARG, "finalize_weights: already finalized");
+    const nb200_config &c = ctx->cfg;
+    const int d = c.d_model, nm = c.num_mel_bins;
+    const std::string E = "model.encoder.", D = "model.decoder.";
+    NB_TRY(up_conv(ctx, E + "conv1.weight", d, nm, &ctx->conv1_w));
+    NB_TRY(up_vec(ctx, E + "conv1.bias", d, &ctx->conv1_b));
+    NB_TRY(up_conv(ctx, E + "conv2.weight", d, d, &ctx->conv2_w));
+    NB_TRY(up_vec(ctx, E + "conv2.bias", d, &ctx->conv2_b));
+    {   // candle `sinusoids` in f32: [sin | cos] halves
+        const int half = d / 2, T = c.max_source_positions;
+        std::vector<float> pos((size_t)T * d);
+        const float inc = logf(10000.0f) / (float)(half - 1);
+        std::vector<float> inv(half);
+        for (int i = 0; i < half; ++i) inv[i] = expf((float)i * (-inc));
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < half; ++i) {
+                float a = (float)t * inv[i];
+                pos[(size_t)t * d + i] = sinf(a);
+                pos[(size_t)t * d + half + i] = cosf(a);
+            }
+        NB_TRY(upload_f32(ctx, pos, &ctx->pos));
+    }
+    ctx->enc.resize(c.encoder_layers);
+    for (int l = 0; l < c.encoder_layers; ++l) {
+        const std::string p = E + "layers." + std::to_string(l) + ".";
+        EncLayer &w = ctx->enc[l];
+        NB_TRY(up_qkv(ctx, p + "self_attn.", d, &w.wqkv, &w.bqkv));
+        NB_TRY(up_mat(ctx, p + "self_attn.out_proj.weight", (size_t)d * d, &w.wo));
+        NB_TRY(up_vec(ctx, p + "self_attn.out_proj.bias", d, &w.bo));
+        NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.weight", d, &w.ln1g));
+        NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.bias", d, &w.ln1b));
+        NB_TRY(up_mat(ctx, p + "fc1.weight", (size_t)4 * d * d, &w.w1));
+        NB_TRY(up_vec(ctx, p + "fc1.bias", 4 * d, &w.b1));
+        NB_TRY(up_mat(ctx, p + "fc2.weight", (size_t)4 * d * d, &w.w2));
+        NB_TRY(up_vec(ctx, p + "fc2.bias", d, &w.b2));
+        NB_TRY(up_vec(ctx, p + "final_layer_norm.weight", d, &w.ln2g));
+        NB_TRY(up_vec(ctx, p + "final_layer_norm.bias", d, &w.ln2b));
+    }
+    NB_TRY(up_vec(ctx, E + "layer_norm.weight", d, &ctx->lnpost_g));
+    NB_TRY(up_vec(ctx, E + "layer_norm.bias", d, &ctx->lnpost_b));
+    // decoder is optional (encoder-only throughput configs): present iff embed_tokens was loaded
+    ctx->has_decoder = c.decoder_layers > 0 && find(ctx, D + "embed_tokens.weight") != nullptr;
+    if (ctx->has_decoder) {
+        NB_TRY(alloc_decoder(ctx));
+        NB_TRY(up_mat(ctx, D + "embed_tokens.weight", (size_t)c.vocab_size * d, &ctx->embed));
+        NB_TRY(up_vec(ctx, D + "embed_positions.weight", (size_t)c.max_target_positions * d, &ctx->embed_pos));
+        ctx->dec.resize(c.decoder_layers);
+        for (int l = 0; l < c.decoder_layers; ++l) {
+            const std::string p = D + "layers." + std::to_string(l) + ".";
+            DecLayer &w = ctx->dec[l];
+            NB_TRY(up_qkv(ctx, p + "self_attn.", d, &w.wqkv, &w.bqkv));
+            NB_TRY(up_mat(ctx, p + "self_attn.out_proj.weight", (size_t)d * d, &w.wo));
+            NB_TRY(up_vec(ctx, p + "self_attn.out_proj.bias", d, &w.bo));
+            NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.weight", d, &w.ln1g));
+            NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.bias", d, &w.ln1b));
+            NB_TRY(up_mat(ctx, p + "encoder_attn.q_proj.weight", (size_t)d * d, &w.cwq));
+            NB_TRY(up_vec(ctx, p + "encoder_attn.q_proj.bias", d, &w.cbq));
+            {   // [k | v] concatenation for the one-shot cross K/V GEMM
+                const HostTensor *k, *v, *bv;
+                NB_TRY(need(ctx, p + "encoder_attn.k_proj.weight", (size_t)d * d, &k));
+                NB_TRY(need(ctx, p + "encoder_attn.v_proj.weight", (size_t)d * d, &v));
+                NB_TRY(need(ctx, p + "encoder_attn.v_proj.bias", d, &bv));
+                std::vector<float> W((size_t)2 * d * d), Bv(2 * d, 0.f);
+                memcpy(W.data(), k->data.data(), (size_t)d * d * 4);
+                memcpy(W.data() + (size_t)d * d, v->data.data(), (size_t)d * d * 4);
+                memcpy(Bv.data() + d, bv->data.data(), d * 4);
+                NB_TRY(upload_compute(ctx, W, &w.cwkv));
+                NB_TRY(upload_f32(ctx, Bv, &w.cbkv));
+            }
+            NB_TRY(up_mat(ctx, p + "encoder_attn.out_proj.weight", (size_t)d * d, &w.cwo));
+            NB_TRY(up_vec(ctx, p + "encoder_attn.out_proj.bias", d, &w.cbo));
+            NB_TRY(up_vec(ctx, p + "encoder_attn_layer_norm.weight", d, &w.lncg));
+            NB_TRY(up_vec(ctx, p + "encoder_attn_layer_norm.bias", d, &w.lncb));
+            NB_TRY(up_mat(ctx, p + "fc1.weight", (size_t)4 * d * d, &w.w1));
+            NB_TRY(up_vec(ctx, p + "fc1.bias", 4 * d, &w.b1));
+            NB_TRY(up_mat(ctx, p + "fc2.weight", (size_t)4 * d * d, &w.w2));
+            NB_TRY(up_vec(ctx, p + "fc2.bias", d, &w.b2));
+            NB_TRY(up_vec(ctx, p + "final_layer_norm.weight", d, &w.ln2g));
+            NB_TRY(up_vec(ctx, p + "final_layer_norm.bias", d, &w.ln2b));
+        }
+        NB_TRY(up_vec(ctx, D + "layer_norm.weight", d, &ctx->lndec_g));
+        NB_TRY(up_vec(ctx, D + "layer_norm.bias", d, &ctx->lndec_b));
+        NB_TRY(upload_suppress(ctx));
+    }
+    ctx->host_tensors.clear();
+    ctx->finalized = true;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_set_mel_filters(nb200_ctx *ctx, const float *filters, int n_mel) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (!filters) return nb200_fail(ctx, NB200_INVALID_ARG, "set_mel_filters: NULL filters");
+    if (n_mel != ctx->cfg.num_mel_bins)
+        return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "Unexpected number of mel bins (num_mel_bins), got: %d", n_mel);
+    NB_TRY(mel_setup_filters(ctx, filters, n_mel));
+    ctx->has_filters = true;
+    return NB200_OK;
+}
+
+int nb200_set_tokens(nb200_ctx *ctx, const nb200_special_tokens *tok) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (!tok) return nb200_fail(ctx, NB200_INVALID_ARG, "set_tokens: NULL");
+    const uint32_t V = (uint32_t)ctx->cfg.vocab_size;
+    if (tok->sot >= V || tok->eot >= V || tok->task >= V || tok->no_speech >= V || tok->no_timestamps >= V || tok->ts_zero >= V || tok->ts_one >= V ||
+        (tok->lang != UINT32_MAX && tok->lang >= V) || tok->ts_zero > tok->ts_one)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "set_tokens: token id out of range for vocab %u", V);
+    ctx->tok = *tok;
+    ctx->has_tokens = true;
+    return upload_suppress(ctx);
+}
+
+int nb200_set_suppress(nb200_ctx *ctx, const uint32_t *ids, size_t n) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (n && !ids) return nb200_fail(ctx, NB200_INVALID_ARG, "set_suppress: NULL ids");
+    ctx->suppress_ids.assign(ids, ids + n);
+    return upload_suppress(ctx);
+}
+
+int nb200_pcm_to_mel_batch(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *mel_out) {
+    NB_TRY(check_ready(ctx, false, true));
+    NB_TRY(stage_pcm(ctx, pcm, n_windows, stride, lens));
+    NB_TRY(launch_mel(ctx, (int)n_windows));
+    NB_TRY(launch_mel_norm(ctx, (int)n_windows));
+    if (mel_out)
+        CUDA_TRY(ctx, cudaMemcpyAsync(mel_out, ctx->mel_norm, n_windows * ctx->cfg.num_mel_bins * N_FRAMES * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_pcm_to_mel(nb200_ctx *ctx, const float *pcm, size_t n, float *mel_out, size_t *n_len) {
+    NB_TRY(check_ready(ctx, false, true));
+    if (n > (size_t)N_SAMPLES) return nb200_fail(ctx, NB200_INVALID_ARG, "pcm_to_mel: %zu samples exceed one window (%d)", n, N_SAMPLES);
+    // candle frame-count rule (SURVEY §8 c-1 rule 3)
+    size_t nl = n / HOP;
+    if (nl % MEL_PAD_FRAMES != 0) nl = (nl / MEL_PAD_FRAMES + 1) * MEL_PAD_FRAMES;
+    nl += MEL_PAD_FRAMES;
+    if (n_len) *n_len = nl;
+    if (!mel_out && !pcm) return NB200_OK;  // pure size query
+    static const float zero = 0.f;
+    size_t len1 = n;
+    NB_TRY(stage_pcm(ctx, n ? pcm : &zero, 1, n ? n : 1, &len1));
+    NB_TRY(launch_mel(ctx, 1));
+    NB_TRY(launch_mel_norm(ctx, 1));
+    if (mel_out) {
+        // frames [0, min(3000, nl)) are computed; frames beyond the data are the normalised value of log10(1e-10)
+        const int nm = ctx->cfg.num_mel_bins;
+        const size_t keep = std::min<size_t>(N_FRAMES, nl);
+        NB_TRY(ensure_pinned(ctx, (size_t)nm * N_FRAMES * 4 + 16));
+        float *hp = (float *)ctx->host_pinned;
+        unsigned *hmax = (unsigned *)(hp + (size_t)nm * N_FRAMES);
+        CUDA_TRY(ctx, cudaMemcpyAsync(hp, ctx->mel_norm, (size_t)nm * N_FRAMES * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(hmax, ctx->mel_max, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        unsigned u = *hmax;
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        float mmax;
+        memcpy(&mmax, &u, 4);
+        const float padv = std::max(-10.0f, mmax - 8.0f) / 4.0f + 1.0f;
+        for (int m = 0; m < nm; ++m) {
+            memcpy(mel_out + (size_t)m * nl, hp + (size_t)m * N_FRAMES, keep * 4);
+            for (size_t f = keep; f < nl; ++f) mel_out[(size_t)m * nl + f] = padv;
+        }
+    } else {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return NB200_OK;
+}
+
+int nb200_encoder_forward(nb200_ctx *ctx, const float *mel, size_t n_windows, float *out) {
+    NB_TRY(check_ready(ctx, true, false));
+    if (n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "encoder_forward: n_windows=%zu (max_batch %d)", n_windows, ctx->cfg.max_batch);
+    if (mel) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mel_norm, mel, n_windows * ctx->cfg.num_mel_bins * N_FRAMES * 4, cudaMemcpyHostToDevice, ctx->stream));
+        NB_TRY(launch_mel_from_host_layout(ctx, (int)n_windows));
+    }
+    NB_TRY(encoder_run(ctx, (int)n_windows));
+    if (out)
+        CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out, n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_transcode_batch(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *out) {
+    NB_TRY(check_ready(ctx, true, true));
+    NB_TRY(stage_pcm(ctx, pcm, n_windows, stride, lens));
+    NB_TRY(launch_mel(ctx, (int)n_windows));
+    NB_TRY(launch_mel_norm(ctx, (int)n_windows));
+    NB_TRY(encoder_run(ctx, (int)n_windows));
+    if (out)
+        CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out, n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_stage_pcm(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens) {
+    NB_TRY(check_ready(ctx, false, false));
+    return stage_pcm(ctx, pcm, n_windows, stride, lens);
+}
+
+int nb200_run_resident(nb200_ctx *ctx, size_t n_windows, int do_mel, int do_encoder) {
+    NB_TRY(check_ready(ctx, do_encoder != 0, do_mel != 0));
+    if (n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch) return nb200_fail(ctx, NB200_INVALID_ARG, "run_resident: n_windows=%zu", n_windows);
+    if (do_mel) {
+        NB_TRY(launch_mel(ctx, (int)n_windows));
+        NB_TRY(launch_mel_norm(ctx, (int)n_windows));
+    }
+    if (do_encoder) NB_TRY(encoder_run(ctx, (int)n_windows));
+    return NB200_OK;  // asynchronous on the ctx stream: pair with nb200_timer_stop / nb200_sync
+}
+
+int nb200_fetch_features(nb200_ctx *ctx, size_t window, float *out, size_t n) {
+    NB_TRY(check_ready(ctx, true, false));
+    const size_t per = (size_t)ctx->cfg.max_source_positions * ctx->cfg.d_model;
+    if (!out || window >= (size_t)ctx->cfg.max_batch || n > per) return nb200_fail(ctx, NB200_INVALID_ARG, "fetch_features: bad argument");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out + window * per, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_fetch_mel(nb200_ctx *ctx, size_t window, float *out, size_t n) {
+    NB_TRY(check_ready(ctx, false, false));
+    const size_t per = (size_t)ctx->cfg.num_mel_bins * N_FRAMES;
+    if (!out || window >= (size_t)ctx->cfg.max_batch || n > per) return nb200_fail(ctx, NB200_INVALID_ARG, "fetch_mel: bad argument");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->mel_norm + window * per, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+static int check_decoder(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, true, false));
+    if (!ctx->has_decoder) return nb200_fail(ctx, NB200_NOT_LOADED, "decoder weights were not loaded");
+    return NB200_OK;
+}
+
+int nb200_decoder_forward(nb200_ctx *ctx, size_t window, const uint32_t *tokens, size_t n, int flush, float *hidden_out) {
+    NB_TRY(check_decoder(ctx));
+    const nb200_config &c = ctx->cfg;
+    if (!tokens || n == 0 || n > (size_t)c.max_target_positions || window >= (size_t)c.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "decoder_forward: n=%zu window=%zu", n, window);
+    if ((int)window >= ctx->n_resident) return nb200_fail(ctx, NB200_NOT_LOADED, "decoder_forward: window %zu has no resident audio features", window);
+    for (size_t i = 0; i < n; ++i)
+        if (tokens[i] >= (uint32_t)c.vocab_size) return nb200_fail(ctx, NB200_INVALID_ARG, "decoder_forward: token %u out of vocab", tokens[i]);
+    if (flush || !ctx->cross_valid) NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
+    const int P = c.max_target_positions, d = c.d_model;
+    int ln = (int)n;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tokens + window * P, tokens, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_len + window, &ln, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // hidden states are gathered in ctx->dff-sized scratch? no: reuse logits buffer (>= 448*d floats only if V >= ..) -> dedicated rows of dhid
+    float *hid_all = nullptr;
+    if (hidden_out) {
+        CUDA_TRY(ctx, cudaMalloc(&hid_all, n * d * 4));
+    }
+    int st = NB200_OK;
+    for (size_t pos = 0; pos < n && st == NB200_OK; ++pos) {
+        st = decoder_step(ctx, (int)window, 1, (int)pos, 0);
+        if (st == NB200_OK && hid_all) st = decoder_copy_hidden(ctx, hid_all + pos * d, d);
+    }
+    if (st == NB200_OK && hid_all) {
+        cudaError_t e = cudaMemcpyAsync(hidden_out, hid_all, n * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) st = nb200_fail(ctx, NB200_CUDA_ERROR, "decoder_forward D2H: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    if (hid_all) cudaFree(hid_all);
+    if (st == NB200_OK && e2 != cudaSuccess) st = nb200_fail(ctx, NB200_CUDA_ERROR, "decoder_forward: %s", cudaGetErrorString(e2));
+    return st;
+}
+
+int nb200_final_linear(nb200_ctx *ctx, const float *hidden, float *logits_out) {
+    NB_TRY(check_decoder(ctx));
+    if (!logits_out) return nb200_fail(ctx, NB200_INVALID_ARG, "final_linear: NULL output");
+    const int d = ctx->cfg.d_model, V = ctx->cfg.vocab_size;
+    if (hidden) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dhid, hidden, d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // logits row 0 = dhid row 0 . embed^T (tied embedding, no bias)
+    {
+        // reuse the step's logits path for one row
+        NB_TRY(decoder_logits_rows(ctx, 1));
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t)V * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_reset_kv_cache(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    ctx->cross_valid = false;
+    return NB200_OK;
+}
+
+int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens, double *avg_logprob,
+                        double *no_speech_prob) {
+    NB_TRY(check_decoder(ctx));
+    const nb200_config &c = ctx->cfg;
+    if (!ctx->has_tokens) return nb200_fail(ctx, NB200_NOT_LOADED, "special tokens not set (call nb200_set_tokens)");
+    if (n_windows == 0 || (int)n_windows > ctx->n_resident || !tokens_out || !n_tokens)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "decode_greedy: n_windows=%zu but %d windows have resident audio features", n_windows, ctx->n_resident);
+    const int B = (int)n_windows, P = c.max_target_positions;
+    const int plen = ctx->tok.lang != UINT32_MAX ? 3 : 2;
+    // `decoder_forward(prompt, audio_features, flush = true)` (model.rs:297-299): rebuild the cross K/V cache
+    NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
+    NB_TRY(decoder_init_state(ctx, B));
+    for (int pos = 0; pos < plen; ++pos) {
+        NB_TRY(decoder_step(ctx, 0, B, pos, pos == 0 || pos == plen - 1));
+        if (pos == 0) NB_TRY(decoder_nospeech(ctx, B));
+    }
+    NB_TRY(decoder_select(ctx, B, (int)max_new_tokens));
+    std::vector<int> done(B);
+    for (int pos = plen; pos < P; ++pos) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        bool all = true;
+        for (int b = 0; b < B; ++b) all &= done[b] != 0;
+        if (all) break;
+        NB_TRY(decoder_step(ctx, 0, B, pos, 1));
+        NB_TRY(decoder_select(ctx, B, (int)max_new_tokens));
+    }
+    std::vector<uint32_t> toks((size_t)B * P);
+    std::vector<int> len(B);
+    std::vector<double> slp(B);
+    std::vector<float> nsp(B);
+    CUDA_TRY(ctx, cudaMemcpyAsync(toks.data(), ctx->d_tokens, toks.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(len.data(), ctx->d_len, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(slp.data(), ctx->d_sumlp, B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(nsp.data(), ctx->d_nospeech, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t nts = ctx->tok.no_timestamps;
+    for (int b = 0; b < B; ++b) {
+        uint32_t *t = toks.data() + (size_t)b * P;
+        int l = len[b];
+        double avg;
+        if (done[b] == 2) {  // no-speech early return: prompt only, avg_logprob = 0 (model.rs:308-315)
+            l = plen;
+            avg = 0.0;
+        } else {
+            avg = slp[b] / (double)l;                      // model.rs:373 (length before the strip)
+            while (l >= 2 && t[l - 2] > nts) {             // model.rs:375-381
+                memmove(t + l - 2, t + l - 1, 4);
+                --l;
+            }
+        }
+        memcpy(tokens_out + (size_t)b * P, t, (size_t)l * 4);
+        for (int i = l; i < P; ++i) tokens_out[(size_t)b * P + i] = 0;
+        n_tokens[b] = (size_t)l;
+        if (avg_logprob) avg_logprob[b] = avg;
+        if (no_speech_prob) no_speech_prob[b] = (double)nsp[b];
+    }
+    return NB200_OK;
+}
+
+int nb200_timer_start(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_timer_stop(nb200_ctx *ctx, float *ms) {
+    NB_TRY(check_ready(ctx, false, false));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop));
+    if (ms) CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return NB200_OK;
+}
+
+int nb200_profile_enable(nb200_ctx *ctx, int on) {
+    NB_TRY(check_ready(ctx, false, false));
+    ctx->profiling = on != 0;
+    return NB200_OK;
+}
+
+static int profile_collect(nb200_ctx *ctx) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->prof_ms[r.cls] += ms;
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+    return NB200_OK;
+}
+
+int nb200_profile_read(nb200_ctx *ctx, float *ms_by_class, int64_t *launches_by_class, double *flops_gemm) {
+    NB_TRY(check_ready(ctx, false, false));
+    NB_TRY(profile_collect(ctx));
+    for (int i = 0; i < NB200_K_COUNT; ++i) {
+        if (ms_by_class) ms_by_class[i] = ctx->prof_ms[i];
+        if (launches_by_class) launches_by_class[i] = ctx->prof_launches[i];
+    }
+    if (flops_gemm) *flops_gemm = ctx->prof_gemm_flops;
+    return NB200_OK;
+}
+
+int nb200_profile_reset(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    NB_TRY(profile_collect(ctx));
+    for (int i = 0; i < NB200_K_COUNT; ++i) { ctx->prof_ms[i] = 0.f; ctx->prof_launches[i] = 0; }
+    ctx->prof_gemm_flops = 0;
+    return NB200_OK;
+}
+
+int nb200_flush_l2(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_test_gemm(nb200_ctx *ctx, const void *a, const void *w, const float *bias, int M, int N, int K, int act_gelu, float *c_out) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (!a || !w || !c_out || M < 1 || N < 1 || K < 1) return nb200_fail(ctx, NB200_INVALID_ARG, "test_gemm: bad argument");
+    const size_t es = dtype_size(ctx->compute);
+    void *dA = nullptr, *dW = nullptr;
+    float *dB = nullptr, *dC = nullptr;
+    int st = [&]() -> int {
+        CUDA_TRY(ctx, cudaMalloc(&dA, (size_t)M * K * es));
+        CUDA_TRY(ctx, cudaMalloc(&dW, (size_t)N * K * es));
+        CUDA_TRY(ctx, cudaMalloc(&dC, (size_t)M * N * 4));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dA, a, (size_t)M * K * es, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dW, w, (size_t)N * K * es, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(dC, 0xff, (size_t)M * N * 4, ctx->stream));
+        if (bias) {
+            CUDA_TRY(ctx, cudaMalloc(&dB, (size_t)N * 4));
+            CUDA_TRY(ctx, cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        GemmShape s{M, 1, N, K, K, (long long)M * K};
+        Epilogue e{};
+        e.bias = dB; e.act = act_gelu; e.out = dC; e.ldo = N; e.out_bf16 = 0;
+        if (ctx->compute == NB200_BF16) NB_TRY(launch_gemm_bf16(ctx, (const bf16 *)dA, (const bf16 *)dW, s, e));
+        else NB_TRY(launch_gemm_f32(ctx, (const float *)dA, (const float *)dW, s, e));
+        CUDA_TRY(ctx, cudaMemcpyAsync(c_out, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    }();
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
+    return st;
+}
+
+int nb200_test_attention(nb200_ctx *ctx, const float *qkv, int B, int T, int n_heads, float *ctx_out) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (!qkv || !ctx_out || B < 1 || T < 1 || n_heads < 1) return nb200_fail(ctx, NB200_INVALID_ARG, "test_attention: bad argument");
+    const int d = n_heads * HEAD_DIM;
+    const size_t nq = (size_t)B * T * 3 * d, no = (size_t)B * T * d;
+    const bool bf = ctx->compute == NB200_BF16;
+    float *dq32 = nullptr, *do32 = nullptr;
+    bf16 *dq16 = nullptr, *do16 = nullptr;
+    int st = [&]() -> int {
+        CUDA_TRY(ctx, cudaMalloc(&dq32, nq * 4));
+        CUDA_TRY(ctx, cudaMalloc(&do32, no * 4));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dq32, qkv, nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (bf) {
+            CUDA_TRY(ctx, cudaMalloc(&dq16, nq * 2));
+            CUDA_TRY(ctx, cudaMalloc(&do16, no * 2));
+            NB_TRY(launch_f32_to_bf16(ctx, dq32, dq16, nq));
+            const char *e = getenv("NB200_ATTN");
+            if (e && !strcmp(e, "simt")) NB_TRY(launch_attention_simt(ctx, dq16, do16, B, T, n_heads, 1));
+            else NB_TRY(launch_attention_tc(ctx, dq16, do16, B, T, n_heads));
+            std::vector<uint16_t> h(no);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), do16, no * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (size_t i = 0; i < no; ++i) ctx_out[i] = bf16_bits_to_float(h[i]);
+        } else {
+            NB_TRY(launch_attention_simt(ctx, dq32, do32, B, T, n_heads, 0));
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx_out, do32, no * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return NB200_OK;
+    }();
+    cudaFree(dq32); cudaFree(do32); cudaFree(dq16); cudaFree(do16);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// common.cuh — shared declarations of libnorma_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/norma_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// Whisper constants norma takes from candle (`m::N_FFT`, `m::HOP_LENGTH`, `m::N_SAMPLES`, `m::N_FRAMES`;
+// used at /root/reference/src/models/whisper/model.rs:69,88)
+constexpr int N_FFT = 400;
+constexpr int HOP = 160;
+constexpr int N_BINS = 201;
+constexpr int N_SAMPLES = 480000;
+constexpr int N_FRAMES = 3000;   // frames kept per window
+constexpr int HEAD_DIM = 64;
+constexpr int MEL_PAD_FRAMES = 1500;  // candle pads n_len by one 15 s chunk of zeros
+
+// ---------------------------------------------------------------------------------------------------------
+// GEMM epilogue description shared by the SIMT fp32 and the tcgen05 bf16 kernels.
+//   v = acc + bias[n];  if (n < n_scale) v *= scale;  if (act) v = gelu_tanh(v);
+//   if (residual) v += residual[b*res_bs + r*ldr + n];   out[b*out_bs + r*ldo + n] = v   (f32 or bf16)
+// Rows are addressed as (batch b, row r < rows_per_batch): this is what lets the conv stem run as a GEMM
+// over overlapping row windows of a time-major buffer without an im2col copy.
+// ---------------------------------------------------------------------------------------------------------
+struct Epilogue {
+    const float *bias;      // [N] or nullptr
+    const float *residual;  // f32 or nullptr (may alias out when out is f32)
+    void *out;
+    long long ldr, res_bs;  // residual row / batch stride (elements)
+    long long ldo, out_bs;  // out row / batch stride (elements)
+    float scale;            // applied to columns [0, n_scale)
+    int n_scale;
+    int act;                // 0 none, 1 gelu(tanh)
+    int out_bf16;           // 1: out is bf16, 0: f32
+};
+
+struct GemmShape {
+    int rows_per_batch;  // M per batch
+    int batch;
+    int N, K;
+    long long lda, a_bs;  // A row / batch stride (elements)
+};
+
+struct EncLayer {
+    void *wqkv, *wo, *w1, *w2;  // compute dtype
+    float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+struct DecLayer {
+    void *wqkv, *wo, *cwq, *cwkv, *cwo, *w1, *w2;
+    float *bqkv, *bo, *cbq, *cbkv, *cbo, *b1, *b2;
+    float *ln1g, *ln1b, *lncg, *lncb, *ln2g, *ln2b;
+};
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct nb200_ctx {
+    int ordinal = 0;
+    nb200_config cfg{};
+    nb200_dtype compute = NB200_BF16;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<void *> allocs;
+    size_t device_bytes = 0;
+    int64_t launches = 0;
+    int sm_count = 148;
+
+    // load state
+    std::map<std::string, HostTensor> host_tensors;
+    bool finalized = false;
+    bool has_filters = false, has_tokens = false;
+    bool has_decoder = false;
+
+    // weights
+    void *conv1_w = nullptr, *conv2_w = nullptr;  // [d][3*n_mel], [d][3*d] (k-major taps, compute dtype)
+    float *conv1_b = nullptr, *conv2_b = nullptr;
+    float *pos = nullptr;  // sinusoids [1500][d] f32
+    std::vector<EncLayer> enc;
+    float *lnpost_g = nullptr, *lnpost_b = nullptr;
+    void *embed = nullptr;       // [V][d] compute dtype
+    float *embed_pos = nullptr;  // [448][d] f32
+    std::vector<DecLayer> dec;
+    float *lndec_g = nullptr, *lndec_b = nullptr;
+
+    // mel
+    float *filt_vals = nullptr;  // banded filterbank: [n_mel][MEL_BAND] values
+    int *filt_start = nullptr;   // [n_mel] first non-zero bin
+    int *filt_len = nullptr;
+    float *mel_tables = nullptr;  // hann[400] | tw200[8*25*2] | tw400[201*2]
+    float *pcm = nullptr;         // [max_batch][N_SAMPLES]
+    int *pcm_len = nullptr;       // [max_batch]
+    float *logmel = nullptr;      // [max_batch][n_mel][N_FRAMES] un-normalised log10
+    unsigned *mel_max = nullptr;  // [max_batch] ordered-uint encoding of the running max
+    float *mel_norm = nullptr;    // [max_batch][n_mel][N_FRAMES] normalised f32 (reference layout)
+    void *melT = nullptr;         // [max_batch][N_FRAMES+2][n_mel] time-major, zero pad rows 0 and N_FRAMES+1
+    size_t *host_lens = nullptr;
+
+    // encoder activations
+    void *y1 = nullptr;     // [max_batch][N_FRAMES+1][d] conv1 out, row 0 = zero pad (compute dtype)
+    float *x = nullptr;     // [max_batch*1500][d] residual stream f32
+    void *h = nullptr;      // [M][d] LN out (compute dtype)
+    void *qkv = nullptr;    // [M][3d]
+    void *attn = nullptr;   // [M][d]
+    void *ff = nullptr;     // [M][4d]
+    float *enc_out = nullptr;  // [M][d] f32 (audio_features)
+    void *enc_out_c = nullptr; // [M][d] compute dtype copy (A operand of the cross-K/V GEMM); == enc_out in f32 mode
+    int n_resident = 0;        // windows with valid features
+
+    // decoder state
+    void *cross_kv = nullptr;  // [L][max_batch][1500][2d]  (k | v), compute dtype
+    void *self_kv = nullptr;   // [L][max_batch][448][2d]
+    bool cross_valid = false;
+    float *dx = nullptr, *dh = nullptr, *dqkv = nullptr, *dattn = nullptr, *dff = nullptr, *dq = nullptr;  // [max_batch][..] f32
+    float *dhid = nullptr;   // [max_batch][d] final LN output
+    float *logits = nullptr; // [max_batch][V]
+    uint32_t *d_tokens = nullptr;  // [max_batch][max_target_positions]
+    int *d_len = nullptr, *d_last_ts = nullptr, *d_done = nullptr, *d_nsampled = nullptr;
+    double *d_sumlp = nullptr;
+    float *d_nospeech = nullptr;
+    float *suppress = nullptr;  // [V] additive mask (0 / -inf): Config::suppress_tokens U {no_timestamps}
+    nb200_special_tokens tok{};
+    std::vector<uint32_t> suppress_ids;
+
+    // misc
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    float prof_ms[NB200_K_COUNT] = {0};
+    int64_t prof_launches[NB200_K_COUNT] = {0};
+    double prof_gemm_flops = 0;
+    void *host_pinned = nullptr;
+    size_t host_pinned_bytes = 0;
+    CUtensorMap *tmap_scratch = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...);
+#define CUDA_TRY(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return nb200_fail(ctx, _e == cudaErrorMemoryAllocation ? NB200_OOM : NB200_CUDA_ERROR,      \
+                              "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define NB_TRY(expr)               \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != NB200_OK) return _s; \
+    } while (0)
+
+// per-kernel-class timing scope (events only when profiling is enabled)
+struct KernelScope {
+    nb200_ctx *ctx;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelScope(nb200_ctx *c, int k);
+    ~KernelScope();
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel launchers (one per .cu file)
+// ---------------------------------------------------------------------------------------------------------
+// mel.cu
+int launch_mel(nb200_ctx *ctx, int n_windows);            // pcm -> logmel (+ running max)
+int launch_mel_norm(nb200_ctx *ctx, int n_windows);       // logmel -> mel_norm (f32, reference layout) + melT
+int launch_mel_from_host_layout(nb200_ctx *ctx, int n_windows);  // mel_norm (already normalised) -> melT
+int mel_setup_tables(nb200_ctx *ctx);
+int mel_setup_filters(nb200_ctx *ctx, const float *filters, int n_mel);
+// simt.cu
+int launch_gemm_f32(nb200_ctx *ctx, const float *A, const float *W, const GemmShape &s, const Epilogue &e);
+int launch_layernorm(nb200_ctx *ctx, const float *x, const float *g, const float *b, int rows, int d, void *out, int out_bf16,
+                     float *out2_f32);
+int launch_attention_simt(nb200_ctx *ctx, const void *qkv, void *out, int B, int T, int n_heads, int is_bf16);
+int launch_f32_to_bf16(nb200_ctx *ctx, const float *in, bf16 *out, size_t n);
+// gemm_tcgen05.cu
+int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmShape &s, const Epilogue &e);
+// attn_tcgen05.cu
+int launch_attention_tc(nb200_ctx *ctx, const bf16 *qkv, bf16 *out, int B, int T, int n_heads);
+// decoder.cu
+int decoder_build_cross_kv(nb200_ctx *ctx, int n_windows);
+int decoder_step(nb200_ctx *ctx, int w0, int n_windows, int pos, int want_logits);  // windows [w0, w0+n); scratch rows 0..n
+int decoder_copy_hidden(nb200_ctx *ctx, float *dst, int d);
+int decoder_init(nb200_ctx *ctx);
+int simt_init(nb200_ctx *ctx);
+int gemm_tc_init(nb200_ctx *ctx);
+int attn_tc_init(nb200_ctx *ctx);
+int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);
+int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens);
+int decoder_nospeech(nb200_ctx *ctx, int n_windows);
+int decoder_init_state(nb200_ctx *ctx, int n_windows);
+// api.cu
+int encoder_run(nb200_ctx *ctx, int n_windows);
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t dtype_size(nb200_dtype t) { return t == NB200_F32 ? 4 : 2; }
+
+// tanh-approximation GELU exactly as candle's `Tensor::gelu`
+__device__ __forceinline__ float gelu_tanh_precise(float x) {
+    const float k0 = 0.7978845608028654f;  // sqrt(2/pi)
+    const float k1 = 0.044715f;
+    float u = k0 * x * (1.0f + k1 * x * x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    const float k0 = 0.7978845608028654f;
+    const float k1 = 0.044715f;
+    float u = k0 * x * (1.0f + k1 * x * x);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    return 0.5f * x * (1.0f + t);
+}
