@@ -31,6 +31,8 @@ def lib():
         _lib.oracle_log_mel_spectrogram.restype = ctypes.c_int
         _lib.oracle_fft.argtypes = [fp, ctypes.c_size_t, fp]
         _lib.oracle_fft.restype = None
+        _lib.oracle_sinusoids.argtypes = [ctypes.c_size_t, ctypes.c_size_t, fp]
+        _lib.oracle_sinusoids.restype = None
     return _lib
 
 
@@ -64,3 +66,9 @@ def fft(x) -> np.ndarray:
     out = np.empty(2 * x.size, np.float32)
     lib().oracle_fft(_fp(x), x.size, _fp(out))
     return out[0::2] + 1j * out[1::2]
+
+
+def sinusoids(length: int, channels: int) -> np.ndarray:
+    out = np.empty((length, channels), np.float32)
+    lib().oracle_sinusoids(length, channels, _fp(out))
+    return out

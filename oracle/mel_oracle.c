@@ -183,3 +183,18 @@ int oracle_pcm_to_mel(const float *pcm, size_t n, const float *filters, size_t n
 
 /* exposed for unit tests of the FFT restatement */
 void oracle_fft(const float *inp, size_t n, float *out) { fft_f32(inp, n, out); }
+
+/* candle `sinusoids(length, channels)` (models::whisper::model) in f32 with libm, as Rust's
+ * f32::ln/exp/sin/cos resolve to on Linux: out [length][channels] = [sin(t*inv) | cos(t*inv)]. */
+void oracle_sinusoids(size_t length, size_t channels, float *out) {
+    size_t half = channels / 2;
+    float max_timescale = 10000.0f;
+    float inc = logf(max_timescale) / (float)(half - 1);
+    for (size_t t = 0; t < length; ++t)
+        for (size_t i = 0; i < half; ++i) {
+            float inv = expf((float)i * (-inc));
+            float a = (float)t * inv;
+            out[t * channels + i] = sinf(a);
+            out[t * channels + half + i] = cosf(a);
+        }
+}

@@ -173,7 +173,14 @@ class Config:
 
 
 def sinusoids(length: int, channels: int) -> torch.Tensor:
-    """candle `sinusoids` (f32): [sin | cos] halves, inv_t[i] = exp(-i * ln(10000)/(channels/2-1))."""
+    """candle `sinusoids` (f32): [sin | cos] halves, inv_t[i] = exp(-i * ln(10000)/(channels/2-1)).
+    Evaluated with libm (oracle/mel_oracle.c) like Rust's f32 intrinsics; at t*inv ~ 1500 rad one ulp of `inv`
+    is 1e-4 in the angle, so the numpy variant below (kept for cross-checks) can differ by that much."""
+    from . import mel_c
+    return torch.from_numpy(mel_c.sinusoids(length, channels))
+
+
+def sinusoids_numpy(length: int, channels: int) -> torch.Tensor:
     inc = np.float32(np.log(np.float32(10000.0))) / np.float32(channels // 2 - 1)
     inv = np.exp((np.arange(channels // 2, dtype=np.float32) * (-inc)).astype(np.float32)).astype(np.float32)
     t = np.arange(length, dtype=np.float32)[:, None] * inv[None, :]
