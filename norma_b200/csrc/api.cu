@@ -245,7 +245,7 @@ int encoder_run(nb200_ctx *ctx, int B) {
     const float qk_scale = powf((float)HEAD_DIM, -0.25f);
     if (g_attn_impl < 0) {
         const char *e = getenv("NB200_ATTN");
-        g_attn_impl = (e && !strcmp(e, "tc")) ? 1 : 0;  // default SIMT until the tcgen05 kernel is validated
+        g_attn_impl = (e && !strcmp(e, "simt")) ? 0 : 1;  // NB200_ATTN=simt selects the CUDA-core kernel (debug)
     }
     auto gemm = [&](const void *A, const void *W, const GemmShape &s, const Epilogue &e) {
         return bf ? launch_gemm_bf16(ctx, (const bf16 *)A, (const bf16 *)W, s, e) : launch_gemm_f32(ctx, (const float *)A, (const float *)W, s, e);

@@ -22,6 +22,7 @@ constexpr int GEMM_THREADS = 256;
 struct GemmTcParams {
     int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
     int rows_per_batch, N;
+    int vec_ok;  // all epilogue pointers / strides allow 16-byte vector access
     Epilogue epi;
 };
 
@@ -35,10 +36,10 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void epi_chunk(const Epilogue &e, const uint32_t *acc, int b, int r, int n0, int N, bool row_ok) {
+__device__ __forceinline__ void epi_chunk(const Epilogue &e, const uint32_t *acc, int b, int r, int n0, int N, bool row_ok, bool vec_ok) {
     if (!row_ok) return;
     float v[32];
-    const bool full = n0 + 32 <= N;
+    const bool full = vec_ok && n0 + 32 <= N;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
     if (e.bias) {
@@ -213,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t acc[32];
                 ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), acc);
                 ptx::tmem_ld_wait();
-                epi_chunk(p.epi, acc, b, r, n0, p.N, row_ok);
+                epi_chunk(p.epi, acc, b, r, n0, p.N, row_ok, p.vec_ok != 0);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -299,6 +300,9 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     p.rows_per_batch = s.rows_per_batch;
     p.N = s.N;
     p.epi = e;
+    const int oa = e.out_bf16 ? 8 : 4;
+    p.vec_ok = (e.ldo % oa == 0) && (e.out_bs % oa == 0) && (((uintptr_t)e.out) % 16 == 0) && (!e.bias || ((uintptr_t)e.bias) % 16 == 0) &&
+               (!e.residual || (e.ldr % 4 == 0 && e.res_bs % 4 == 0 && ((uintptr_t)e.residual) % 16 == 0));
     const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
     KernelScope ks(ctx, NB200_K_GEMM);
     ctx->prof_gemm_flops += 2.0 * s.batch * s.rows_per_batch * (double)s.N * s.K;
