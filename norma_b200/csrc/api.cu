@@ -22,7 +22,7 @@ int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
-KernelScope::KernelScope(nb200_ctx *c, int k) : ctx(c), cls(k) {
+KernelScope::KernelScope(nb200_ctx *c, int k, long long tag_) : ctx(c), cls(k), tag(tag_) {
     ctx->launches++;
     ctx->prof_launches[cls]++;
     if (ctx->profiling) {
@@ -40,7 +40,7 @@ KernelScope::KernelScope(nb200_ctx *c, int k) : ctx(c), cls(k) {
 KernelScope::~KernelScope() {
     if (a) {
         cudaEventRecord(b, ctx->stream);
-        ctx->prof_recs.push_back({cls, a, b});
+        ctx->prof_recs.push_back({cls, a, b, tag});
     }
 }
 
@@ -844,7 +844,12 @@ static int profile_collect(nb200_ctx *ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto &r : ctx->prof_recs) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) ctx->prof_ms[r.cls] += ms;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ctx->prof_ms[r.cls] += ms;
+            auto &t = ctx->prof_by_tag[(long long)r.cls * 1000000000000LL + r.tag];
+            t.first += ms;
+            t.second += 1;
+        }
         ctx->ev_pool.push_back(r.a);
         ctx->ev_pool.push_back(r.b);
     }
@@ -860,6 +865,11 @@ int nb200_profile_read(nb200_ctx *ctx, float *ms_by_class, int64_t *launches_by_
         if (launches_by_class) launches_by_class[i] = ctx->prof_launches[i];
     }
     if (flops_gemm) *flops_gemm = ctx->prof_gemm_flops;
+    if (getenv("NB200_PROF_DUMP")) {
+        for (auto &kv : ctx->prof_by_tag)
+            fprintf(stderr, "[nb200 prof] class %lld tag %lld: %.3f ms over %lld launches (%.1f us each)\n", kv.first / 1000000000000LL,
+                    kv.first % 1000000000000LL, kv.second.first, kv.second.second, 1e3 * kv.second.first / (double)kv.second.second);
+    }
     return NB200_OK;
 }
 
@@ -868,6 +878,7 @@ int nb200_profile_reset(nb200_ctx *ctx) {
     NB_TRY(profile_collect(ctx));
     for (int i = 0; i < NB200_K_COUNT; ++i) { ctx->prof_ms[i] = 0.f; ctx->prof_launches[i] = 0; }
     ctx->prof_gemm_flops = 0;
+    ctx->prof_by_tag.clear();
     return NB200_OK;
 }
 
@@ -901,6 +912,41 @@ int nb200_test_gemm(nb200_ctx *ctx, const void *a, const void *w, const float *b
         else NB_TRY(launch_gemm_f32(ctx, (const float *)dA, (const float *)dW, s, e));
         CUDA_TRY(ctx, cudaMemcpyAsync(c_out, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return NB200_OK;
+    }();
+    cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
+    return st;
+}
+
+int nb200_test_gemm_perf(nb200_ctx *ctx, int M, int N, int K, int epi_kind, int iters, float *ms_out) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (ctx->compute != NB200_BF16 || !ms_out || iters < 1) return nb200_fail(ctx, NB200_INVALID_ARG, "test_gemm_perf: bf16 ctx required");
+    bf16 *dA = nullptr, *dW = nullptr;
+    float *dB = nullptr;
+    void *dC = nullptr;
+    int st = [&]() -> int {
+        CUDA_TRY(ctx, cudaMalloc(&dA, (size_t)M * K * 2));
+        CUDA_TRY(ctx, cudaMalloc(&dW, (size_t)N * K * 2));
+        CUDA_TRY(ctx, cudaMalloc(&dB, (size_t)N * 4));
+        CUDA_TRY(ctx, cudaMalloc(&dC, (size_t)M * N * 4));
+        CUDA_TRY(ctx, cudaMemsetAsync(dA, 0, (size_t)M * K * 2, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(dW, 0, (size_t)N * K * 2, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(dB, 0, (size_t)N * 4, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(dC, 0, (size_t)M * N * 4, ctx->stream));
+        GemmShape s{M, 1, N, K, K, (long long)M * K};
+        Epilogue e{};
+        e.bias = dB; e.out = dC; e.ldo = N;
+        if (epi_kind == 0) { e.out_bf16 = 1; }
+        else if (epi_kind == 1) { e.out_bf16 = 1; e.act = 1; }
+        else { e.out_bf16 = 0; e.residual = (const float *)dC; e.ldr = N; }
+        for (int i = 0; i < 3; ++i) NB_TRY(launch_gemm_bf16(ctx, dA, dW, s, e));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+        for (int i = 0; i < iters; ++i) NB_TRY(launch_gemm_bf16(ctx, dA, dW, s, e));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        *ms_out = ms / iters;
         return NB200_OK;
     }();
     cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);

@@ -136,7 +136,8 @@ struct nb200_ctx {
     size_t flush_bytes = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool profiling = false;
-    struct ProfRec { int cls; cudaEvent_t a, b; };
+    struct ProfRec { int cls; cudaEvent_t a, b; long long tag; };
+    std::map<long long, std::pair<double, long long>> prof_by_tag;  // debug: per (class, shape) time
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[NB200_K_COUNT] = {0};
@@ -169,7 +170,8 @@ struct KernelScope {
     nb200_ctx *ctx;
     int cls;
     cudaEvent_t a = nullptr, b = nullptr;
-    KernelScope(nb200_ctx *c, int k);
+    long long tag = 0;
+    KernelScope(nb200_ctx *c, int k, long long tag_ = 0);
     ~KernelScope();
 };
 

@@ -4,79 +4,78 @@
 // decoder's cross-attention K/V build.  Replaces candle's cuBLAS-SGEMM + separate bias/GELU/add kernels reached
 // from /root/reference/src/models/whisper/model.rs:455-464.
 //
-// Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0   TMA producer: A tile 128 x 64 and W tile BN x 64 (bf16, K-major, SWIZZLE_128B) per stage
-//   warp 1   MMA issuer:   one elected thread, tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16,
-//                          accumulators in TMEM (2 stages x BN columns: epilogue of tile i overlaps mainloop of i+1)
-//   warp 2   TMEM alloc / dealloc
-//   warps 4-7 epilogue:    tcgen05.ld 32x32b (thread = accumulator row), fused math, vectorised global stores
+// Structure (persistent, warp-specialised, one CTA per SM, 384 threads):
+//   warp 0     TMA producer: A tile 128 x 64 and W tile (bf16, K-major, SWIZZLE_128B) per stage
+//   warp 1     MMA issuer: one thread, tcgen05.mma kind::f16, accumulators in TMEM, 2 stages x BN columns so the
+//              epilogue of tile i overlaps the mainloop of tile i+1
+//   warp 2     TMEM alloc / dealloc
+//   warps 4-11 epilogue (2 per scheduler, alternate column chunks): thread = accumulator row (TMEM lane).  tcgen05.ld -> fused math -> the warp's 32-row x 128-byte
+//              chunk is written to a swizzled smem patch and leaves with ONE bulk tensor store (TMA); the f32
+//              residual chunk arrives the same way (TMA load, first chunk issued before the accumulator is ready,
+//              later chunks one ahead).  Thread-per-row global stores were measured to cap at ~1.2 TB/s of 16-byte
+//              L2 write requests and made every K = 1280 GEMM epilogue-bound (profiles/).
+// CTA2 = true is the cta_group::2 variant: a CTA pair (cluster 2x1) owns a 256 x BN tile; each CTA loads its own
+// 128 A rows and HALF of the W tile, the leader issues UMMA 256 x BN x 16 over both CTAs' shared memory (operand
+// traffic per FLOP / 1.5 against the 128 x 256 single-CTA tile), accumulator rows [128r, 128r+128) live in CTA r.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+constexpr int STG_BYTES = 4096;  // one staging patch: 32 rows x 128 B
 
 struct GemmTcParams {
     int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
     int rows_per_batch, N;
-    int vec_ok;  // all epilogue pointers / strides allow 16-byte vector access
+    int vec_ok;   // direct epilogue: all pointers / strides allow 16-byte vector access
+    int use_tma;  // TMA-store epilogue (needs 16-byte aligned rows); 0 = direct thread-per-row stores
+    int res_b0;   // residual has no batch dimension (positional table): always batch coordinate 0
+    int debug;    // microbenchmark switches: 1 = epilogue touches no global memory, 2 = no TMA / MMA mainloop
     Epilogue epi;
 };
 
-template <int BN>
+template <int BN, bool CTA2>
 struct GemmCfg {
-    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;  // W rows this CTA loads per stage
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (STAGE_BYTES == 49152) ? 3 : 5;
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TILE_M = CTA2 ? 256 : 128;
+    static constexpr int STAGING = EPI_WARPS * 2 * STG_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may opt in to");
 };
 
-__device__ __forceinline__ void epi_chunk(const Epilogue &e, const uint32_t *acc, int b, int r, int n0, int N, bool row_ok, bool vec_ok) {
+__device__ __forceinline__ float epi_math(float acc, float bias, float cs, int act) {
+    float v = (acc + bias) * cs;
+    if (act) v = gelu_tanh_fast(v);
+    return v;
+}
+
+// ---- fallback epilogue: thread-per-row direct global access (arbitrary alignment) -------------------------------
+__device__ __forceinline__ void epi_chunk_direct(const Epilogue &e, const uint32_t *acc, int b, int r, int n0, int N, bool row_ok, bool vec_ok) {
     if (!row_ok) return;
-    float v[32];
     const bool full = vec_ok && n0 + 32 <= N;
+    float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    if (e.bias) {
-        if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 bb = __ldg((const float4 *)(e.bias + n0 + j));
-                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < N) v[j] += __ldg(e.bias + n0 + j);
-        }
-    }
-    if (n0 < e.n_scale) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (n0 + j < e.n_scale) v[j] *= e.scale;
-    }
-    if (e.act) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+    for (int j = 0; j < 32; ++j) {
+        float bias = (e.bias && n0 + j < N) ? __ldg(e.bias + n0 + j) : 0.f;
+        v[j] = epi_math(__uint_as_float(acc[j]), bias, (n0 + j < e.n_scale) ? e.scale : 1.0f, e.act);
     }
     if (e.residual) {
         const float *rp = e.residual + (long long)b * e.res_bs + (long long)r * e.ldr + n0;
-        if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 rr = *(const float4 *)(rp + j);
-                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < N) v[j] += rp[j];
-        }
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < N) v[j] += rp[j];
     }
     const long long o = (long long)b * e.out_bs + (long long)r * e.ldo + n0;
     if (e.out_bf16) {
@@ -108,27 +107,50 @@ __device__ __forceinline__ void epi_chunk(const Epilogue &e, const uint32_t *acc
     }
 }
 
-template <int BN>
+// bias for 4 consecutive columns (guarded at the N edge)
+__device__ __forceinline__ float4 bias4(const Epilogue &e, int n, int N, bool full) {
+    if (!e.bias) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (full) return __ldg((const float4 *)(e.bias + n));
+    float4 b;
+    b.x = n + 0 < N ? __ldg(e.bias + n + 0) : 0.f;
+    b.y = n + 1 < N ? __ldg(e.bias + n + 1) : 0.f;
+    b.z = n + 2 < N ? __ldg(e.bias + n + 2) : 0.f;
+    b.w = n + 3 < N ? __ldg(e.bias + n + 3) : 0.f;
+    return b;
+}
+
+template <int BN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
-    using C = GemmCfg<BN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmRes, const GemmTcParams p) {
+    using C = GemmCfg<BN, CTA2>;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_raw_u = ptx::smem_u32(smem_raw);
+    const uint32_t smem_base = (smem_raw_u + 1023u) & ~1023u;
     const uint32_t sA = smem_base, sB = smem_base + C::STAGES * C::A_BYTES;
-    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
-    // barrier layout (8 B each): full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr (4 B)
+    const uint32_t stg_base = smem_base + C::STAGES * C::STAGE_BYTES;  // 1024-aligned
+    const uint32_t bars = stg_base + C::STAGING;
+    // barrier layout (8 B each): full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem_ptr | res_full[EPI_WARPS][2]
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
     const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
-    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+    auto res_bar = [&](int w, int buf) { return bars + 8u * (2 * C::STAGES + 5 + 2 * w + buf); };
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_raw_u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;
+    const int first_tile = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
         ptx::prefetch_tmap(&tmB);
+        if (p.use_tma) {
+            ptx::prefetch_tmap(&tmOut);
+            if (p.epi.residual) ptx::prefetch_tmap(&tmRes);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -137,96 +159,257 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);
+            ptx::mbar_init(tempty_bar(s), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);  // CTA2: both CTAs' warps arrive on the LEADER
+        }
+        for (int w = 0; w < EPI_WARPS; ++w) {
+            ptx::mbar_init(res_bar(w, 0), 1);
+            ptx::mbar_init(res_bar(w, 1), 1);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (CTA2) {
+            ptx::tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+            ptx::tmem_relinquish_2sm();
+        } else {
+            ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync();  // both CTAs' barriers are initialised before any remote signal
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    const int k_blocks = (p.debug & 2) ? 0 : p.k_blocks;
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
                 const int n_idx = tile % p.n_tiles, mb = tile / p.n_tiles;
                 const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                    ptx::tma_load_3d(sA + stage * C::A_BYTES, &tmA, full_bar(stage), kb * BK, mt * BM, b);
-                    ptx::tma_load_2d(sB + stage * C::B_BYTES, &tmB, full_bar(stage), kb * BK, n_idx * BN);
+                    if (CTA2) {
+                        if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);  // bytes of both CTAs
+                        const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                        ptx::tma_load_3d_2sm(sA + stage * C::A_BYTES, &tmA, lead_full, kb * BK, mt * 256 + (int)rank * BM, b);
+                        ptx::tma_load_2d_2sm(sB + stage * C::B_BYTES, &tmB, lead_full, kb * BK, n_idx * BN + (int)rank * (BN / 2));
+                    } else {
+                        ptx::mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                        ptx::tma_load_3d(sA + stage * C::A_BYTES, &tmA, full_bar(stage), kb * BK, mt * BM, b);
+                        ptx::tma_load_2d(sB + stage * C::B_BYTES, &tmB, full_bar(stage), kb * BK, n_idx * BN);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, 0, 0);
+        // ================= MMA issuer (leader CTA only when paired) =================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(C::TILE_M, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(full_bar(stage), phase);
                     ptx::tc_fence_after();
                     const uint64_t da = ptx::make_sw128_desc(sA + stage * C::A_BYTES, 16, 1024);
                     const uint64_t db = ptx::make_sw128_desc(sB + stage * C::B_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)  // +32 B per UMMA_K step inside the 128 B swizzle atom
-                        ptx::mma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    ptx::mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+                    for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K step inside the 128 B swizzle atom
+                        if (CTA2) ptx::mma_bf16_ss_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else ptx::mma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    if (CTA2) ptx::mma_commit_2sm_mc(empty_bar(stage), 3);  // frees the stage in both CTAs
+                    else ptx::mma_commit(empty_bar(stage));
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::mma_commit(tfull_bar(as));  // accumulator complete
+                if (CTA2) ptx::mma_commit_2sm_mc(tfull_bar(as), 3);  // accumulator complete
+                else ptx::mma_commit(tfull_bar(as));
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ================= epilogue: 8 warps = 2 per scheduler; warps (4+q) and (8+q) share TMEM lane quarter q and take
+        // alternate column chunks =================
+        const int ew = warp - 4;
+        const int q = warp & 3;      // TMEM lane quarter this warp may access
+        const int grp = ew >> 2;     // 0 / 1: even / odd chunks
+        const Epilogue &e = p.epi;
+        const bool has_res = e.residual != nullptr;
+        const bool no_mem = (p.debug & 1) != 0;
+        const uint32_t stg = stg_base + (uint32_t)(ew * 2 * STG_BYTES);
+        uint8_t *stg_ptr = smem_raw + (stg - smem_raw_u);
+        const int sw = lane & 7;
+        uint32_t rphase = 0;  // bit b: parity of res_bar(ew, b)
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
             const int n_idx = tile % p.n_tiles, mb = tile / p.n_tiles;
             const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
-            const int r = mt * BM + q * 32 + lane;
-            const bool row_ok = r < p.rows_per_batch;
-            ptx::mbar_wait(tfull_bar(as), aphase);
-            ptx::tc_fence_after();
+            const int r0 = mt * C::TILE_M + (int)rank * BM + q * 32;  // this warp's first row
+            const int nt0 = n_idx * BN;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            const int rb = p.res_b0 ? 0 : b;
+            if (p.use_tma && !no_mem) {
+                if (e.out_bf16) {
+                    // ---------- bf16 out: 64-column chunks (128 B rows), no residual ----------
+                    ptx::mbar_wait(tfull_bar(as), aphase);
+                    ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int n0 = n_idx * BN + c * 32;
-                if (n0 >= p.N) break;  // warp-uniform
-                uint32_t acc[32];
-                ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), acc);
-                ptx::tmem_ld_wait();
-                epi_chunk(p.epi, acc, b, r, n0, p.N, row_ok, p.vec_ok != 0);
+                    for (int ci = 0; ci < BN / 128; ++ci) {
+                        const int c = 2 * ci + grp;
+                        const int n0 = nt0 + c * 64;
+                        if (n0 >= p.N) continue;  // warp-uniform
+                        const uint32_t sb = stg + (uint32_t)((ci & 1) * STG_BYTES);
+                        uint8_t *sbp = stg_ptr + (ci & 1) * STG_BYTES + lane * 128;
+                        uint32_t acc[64];
+                        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
+                        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), acc + 32);
+                        if (lane == 0) ptx::bulk_wait_read<1>();  // the store that used this patch two chunks ago is done reading
+                        __syncwarp();
+                        const bool full = n0 + 64 <= p.N;
+                        const bool mixed = n0 < e.n_scale && n0 + 64 > e.n_scale;
+                        const float cs = (n0 + 64 <= e.n_scale) ? e.scale : 1.0f;
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [8j, 8j+8)
+                            const float4 b0 = bias4(e, n0 + 8 * j, p.N, full), b1 = bias4(e, n0 + 8 * j + 4, p.N, full);
+                            float v[8];
+                            v[0] = (__uint_as_float(acc[8 * j + 0]) + b0.x) * cs; v[1] = (__uint_as_float(acc[8 * j + 1]) + b0.y) * cs;
+                            v[2] = (__uint_as_float(acc[8 * j + 2]) + b0.z) * cs; v[3] = (__uint_as_float(acc[8 * j + 3]) + b0.w) * cs;
+                            v[4] = (__uint_as_float(acc[8 * j + 4]) + b1.x) * cs; v[5] = (__uint_as_float(acc[8 * j + 5]) + b1.y) * cs;
+                            v[6] = (__uint_as_float(acc[8 * j + 6]) + b1.z) * cs; v[7] = (__uint_as_float(acc[8 * j + 7]) + b1.w) * cs;
+                            if (mixed) {  // a chunk straddling the scaled-column boundary (not hit by the Whisper shapes)
+#pragma unroll
+                                for (int t = 0; t < 8; ++t)
+                                    if (n0 + 8 * j + t < e.n_scale) v[t] *= e.scale;
+                            }
+                            if (e.act) {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) v[t] = gelu_tanh_fast(v[t]);
+                            }
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                            uint4 pk;
+                            pk.x = *(unsigned *)&p0; pk.y = *(unsigned *)&p1; pk.z = *(unsigned *)&p2; pk.w = *(unsigned *)&p3;
+                            *(uint4 *)(sbp + ((j ^ sw) << 4)) = pk;
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_3d(&tmOut, sb, n0, r0, b);
+                            ptx::bulk_commit();
+                        }
+                    }
+                } else {
+                    // ---------- f32 out: 32-column chunks (128 B rows), optional f32 residual via TMA ----------
+                    constexpr int NCI = BN / 64;  // chunks per warp
+                    if (has_res && lane == 0 && nt0 + grp * 32 < p.N) {  // first chunk's residual is fetched while the mainloop still runs
+                        ptx::bulk_wait_read<0>();
+                        ptx::mbar_expect_tx(res_bar(ew, 0), STG_BYTES);
+                        ptx::tma_load_3d(stg, &tmRes, res_bar(ew, 0), nt0 + grp * 32, r0, rb);
+                    }
+                    ptx::mbar_wait(tfull_bar(as), aphase);
+                    ptx::tc_fence_after();
+#pragma unroll 1
+                    for (int ci = 0; ci < NCI; ++ci) {
+                        const int c = 2 * ci + grp;
+                        const int n0 = nt0 + c * 32;
+                        if (n0 >= p.N) continue;  // warp-uniform
+                        const int buf = ci & 1;
+                        const uint32_t sb = stg + (uint32_t)(buf * STG_BYTES);
+                        uint8_t *sbp = stg_ptr + buf * STG_BYTES + lane * 128;
+                        uint32_t acc[32];
+                        ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), acc);
+                        if (has_res) {
+                            if (lane == 0 && ci + 1 < NCI && n0 + 64 < p.N) {  // this warp's next chunk, one ahead
+                                ptx::bulk_wait_read<0>();  // its previous store no longer reads the other patch
+                                ptx::mbar_expect_tx(res_bar(ew, buf ^ 1), STG_BYTES);
+                                ptx::tma_load_3d(stg + (uint32_t)((buf ^ 1) * STG_BYTES), &tmRes, res_bar(ew, buf ^ 1), n0 + 64, r0, rb);
+                            }
+                            ptx::mbar_wait(res_bar(ew, buf), (rphase >> buf) & 1u);
+                            rphase ^= 1u << buf;
+                        } else {
+                            if (lane == 0) ptx::bulk_wait_read<1>();
+                            __syncwarp();
+                        }
+                        const bool full = n0 + 32 <= p.N;
+                        const bool mixed = n0 < e.n_scale && n0 + 32 > e.n_scale;
+                        const float cs = (n0 + 32 <= e.n_scale) ? e.scale : 1.0f;
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [4j, 4j+4)
+                            const float4 bb = bias4(e, n0 + 4 * j, p.N, full);
+                            float v[4];
+                            v[0] = (__uint_as_float(acc[4 * j + 0]) + bb.x) * cs; v[1] = (__uint_as_float(acc[4 * j + 1]) + bb.y) * cs;
+                            v[2] = (__uint_as_float(acc[4 * j + 2]) + bb.z) * cs; v[3] = (__uint_as_float(acc[4 * j + 3]) + bb.w) * cs;
+                            if (mixed) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (n0 + 4 * j + t < e.n_scale) v[t] *= e.scale;
+                            }
+                            if (e.act) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) v[t] = gelu_tanh_fast(v[t]);
+                            }
+                            float4 *sp = (float4 *)(sbp + ((j ^ sw) << 4));
+                            if (has_res) {
+                                const float4 rr = *sp;
+                                v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+                            }
+                            *sp = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_3d(&tmOut, sb, n0, r0, b);
+                            ptx::bulk_commit();
+                        }
+                    }
+                }
+            } else {
+                // ---------- direct thread-per-row epilogue (unaligned shapes; also the no-memory microbenchmark mode) ----------
+                const int r = r0 + lane;
+                const bool row_ok = r < p.rows_per_batch && !no_mem;
+                ptx::mbar_wait(tfull_bar(as), aphase);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int c = grp; c < BN / 32; c += 2) {
+                    const int n0 = nt0 + c * 32;
+                    if (n0 >= p.N) break;
+                    uint32_t acc[32];
+                    ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), acc);
+                    ptx::tmem_ld_wait();
+                    epi_chunk_direct(e, acc, b, r, n0, p.N, row_ok, p.vec_ok != 0);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (CTA2) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(as), 0));
+                else ptx::mbar_arrive(tempty_bar(as));
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        if (lane == 0) ptx::bulk_wait_all();  // every bulk store of this thread has been written
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync();  // nobody leaves (or frees TMEM) while the peer can still signal into this CTA
+    else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if (CTA2) ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -235,10 +418,8 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuui
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_tmapEncodeTiled g_encode = nullptr;
 
-}  // namespace
-
-int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                     const uint32_t *box) {
+int tmap_encode(nb200_ctx *ctx, CUtensorMap *out, CUtensorMapDataType dt, const void *base, int rank, const uint64_t *dims,
+                const uint64_t *strides_bytes, const uint32_t *box) {
     if (!g_encode) {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -255,9 +436,8 @@ int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int ran
         es[i] = 1;
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode(out, dt, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return nb200_fail(ctx, NB200_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu strides %llu,%llu box %u,%u", (int)r,
                           rank, (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull,
@@ -265,9 +445,36 @@ int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int ran
     return NB200_OK;
 }
 
+// cluster launch of the paired kernel (the cluster shape is a launch attribute, so one kernel template serves both)
+template <int BN>
+cudaError_t launch_pair(int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const CUtensorMap &r,
+                        const GemmTcParams &p) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true>, a, b, o, r, p);
+}
+
+}  // namespace
+
+int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                     const uint32_t *box) {
+    return tmap_encode(ctx, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
 int gemm_tc_init(nb200_ctx *ctx) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, false>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true>::SMEM_BYTES));
     return NB200_OK;
 }
 
@@ -275,11 +482,39 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     if (s.lda % 8 != 0 || s.a_bs % 8 != 0 || s.K % 8 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)W & 15))
         return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "gemm_bf16: operands must be 16-byte aligned (K=%d lda=%lld a_bs=%lld)", s.K, s.lda,
                           s.a_bs);
-    // BN = 256 unless N is small enough that 128-wide tiles give a better wave fit
-    const int m_tiles = ceil_div(s.rows_per_batch, BM) * s.batch;
-    const bool use128 = (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128;
+    static int mode = -1, epi = -1;  // NB200_GEMM=1cta: single-CTA kernel; NB200_EPI=direct: thread-per-row stores (A/B comparison)
+    if (mode < 0) {
+        const char *ev = getenv("NB200_GEMM");
+        mode = (ev && !strcmp(ev, "1cta")) ? 1 : 2;
+        ev = getenv("NB200_EPI");
+        epi = (ev && !strcmp(ev, "direct")) ? 0 : 1;
+    }
+    const bool pair = mode == 2 && s.N >= 256;
+    // single-CTA: BN = 256 unless N is small enough that 128-wide tiles give a better wave fit
+    const bool use128 = !pair && ((s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
     const int BN = use128 ? 128 : 256;
-    CUtensorMap tmA, tmB;
+    const int tile_m = pair ? 256 : BM;
+    GemmTcParams p;
+    p.m_tiles_per_batch = ceil_div(s.rows_per_batch, tile_m);
+    p.n_tiles = ceil_div(s.N, BN);
+    p.total_tiles = p.m_tiles_per_batch * s.batch * p.n_tiles;
+    p.k_blocks = ceil_div(s.K, BK);
+    p.rows_per_batch = s.rows_per_batch;
+    p.N = s.N;
+    p.epi = e;
+    {
+        const char *dv = getenv("NB200_GEMM_DEBUG");
+        p.debug = dv ? atoi(dv) : 0;
+    }
+    const int oes = e.out_bf16 ? 2 : 4;
+    const int oa = 16 / oes;
+    p.vec_ok = (e.ldo % oa == 0) && (e.out_bs % oa == 0) && (((uintptr_t)e.out) % 16 == 0) && (!e.bias || ((uintptr_t)e.bias) % 16 == 0) &&
+               (!e.residual || (e.ldr % 4 == 0 && e.res_bs % 4 == 0 && ((uintptr_t)e.residual) % 16 == 0));
+    // the TMA epilogue handles (bf16 out, no residual) and (f32 out, optional f32 residual) on 16-byte aligned rows
+    p.use_tma = epi == 1 && p.vec_ok && !(e.out_bf16 && e.residual) && e.ldo > 0;
+    p.res_b0 = (e.residual && (s.batch == 1 || e.res_bs == 0)) ? 1 : 0;
+
+    CUtensorMap tmA, tmB, tmOut, tmRes;
     {
         uint64_t dims[3] = {(uint64_t)s.K, (uint64_t)s.rows_per_batch, (uint64_t)s.batch};
         uint64_t str[2] = {(uint64_t)s.lda * 2, (uint64_t)(s.batch > 1 ? s.a_bs : (long long)s.lda * s.rows_per_batch) * 2};
@@ -289,27 +524,37 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     {
         uint64_t dims[2] = {(uint64_t)s.K, (uint64_t)s.N};
         uint64_t str[1] = {(uint64_t)s.K * 2};
-        uint32_t box[2] = {BK, (uint32_t)BN};
+        uint32_t box[2] = {BK, (uint32_t)(pair ? BN / 2 : BN)};
         NB_TRY(tmap_encode_bf16(ctx, &tmB, W, 2, dims, str, box));
     }
-    GemmTcParams p;
-    p.m_tiles_per_batch = ceil_div(s.rows_per_batch, BM);
-    p.n_tiles = ceil_div(s.N, BN);
-    p.total_tiles = m_tiles * p.n_tiles;
-    p.k_blocks = ceil_div(s.K, BK);
-    p.rows_per_batch = s.rows_per_batch;
-    p.N = s.N;
-    p.epi = e;
-    const int oa = e.out_bf16 ? 8 : 4;
-    p.vec_ok = (e.ldo % oa == 0) && (e.out_bs % oa == 0) && (((uintptr_t)e.out) % 16 == 0) && (!e.bias || ((uintptr_t)e.bias) % 16 == 0) &&
-               (!e.residual || (e.ldr % 4 == 0 && e.res_bs % 4 == 0 && ((uintptr_t)e.residual) % 16 == 0));
-    const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-    KernelScope ks(ctx, NB200_K_GEMM);
+    tmOut = tmA;
+    tmRes = tmA;
+    if (p.use_tma) {
+        {
+            uint64_t dims[3] = {(uint64_t)s.N, (uint64_t)s.rows_per_batch, (uint64_t)s.batch};
+            uint64_t str[2] = {(uint64_t)e.ldo * oes, (uint64_t)(s.batch > 1 ? e.out_bs : e.ldo * (long long)s.rows_per_batch) * oes};
+            uint32_t box[3] = {(uint32_t)(128 / oes), 32, 1};
+            NB_TRY(tmap_encode(ctx, &tmOut, e.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e.out, 3, dims, str, box));
+        }
+        if (e.residual) {
+            const bool b0 = p.res_b0 != 0;
+            uint64_t dims[3] = {(uint64_t)s.N, (uint64_t)s.rows_per_batch, (uint64_t)(b0 ? 1 : s.batch)};
+            uint64_t str[2] = {(uint64_t)e.ldr * 4, (uint64_t)(b0 ? e.ldr * (long long)s.rows_per_batch : e.res_bs) * 4};
+            uint32_t box[3] = {32, 32, 1};
+            NB_TRY(tmap_encode(ctx, &tmRes, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, e.residual, 3, dims, str, box));
+        }
+    }
+    KernelScope ks(ctx, NB200_K_GEMM, (long long)s.N * 100000 + s.K);
     ctx->prof_gemm_flops += 2.0 * s.batch * s.rows_per_batch * (double)s.N * s.K;
-    if (BN == 256)
-        gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
-    else
-        gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+    if (pair) {
+        const int max_cl = ctx->sm_count / 2;
+        const int clusters = p.total_tiles < max_cl ? p.total_tiles : max_cl;
+        CUDA_TRY(ctx, launch_pair<256>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p));
+    } else {
+        const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+        if (BN == 256) gemm_tc_kernel<256, false><<<grid, GEMM_THREADS, GemmCfg<256, false>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
+        else gemm_tc_kernel<128, false><<<grid, GEMM_THREADS, GemmCfg<128, false>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;
 }

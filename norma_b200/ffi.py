@@ -25,7 +25,7 @@ SYMBOLS = [
     "nb200_pcm_to_mel", "nb200_pcm_to_mel_batch", "nb200_encoder_forward", "nb200_transcode_batch", "nb200_stage_pcm",
     "nb200_run_resident", "nb200_fetch_features", "nb200_fetch_mel", "nb200_decoder_forward", "nb200_final_linear",
     "nb200_reset_kv_cache", "nb200_decode_greedy", "nb200_timer_start", "nb200_timer_stop", "nb200_profile_enable",
-    "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_attention",
+    "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_gemm_perf", "nb200_test_attention",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
         "nb200_profile_reset": ([p], i),
         "nb200_flush_l2": ([p], i),
         "nb200_test_gemm": ([p, p, p, f32p, i, i, i, i, f32p], i),
+        "nb200_test_gemm_perf": ([p, i, i, i, i, i, f32p], i),
         "nb200_test_attention": ([p, f32p, i, i, i, f32p], i),
     }
     for name, (args, res) in sigs.items():
@@ -315,6 +316,11 @@ class Context:
         out = np.empty((M, N), np.float32)
         self._ck(self.lib.nb200_test_gemm(self.h, a_.ctypes.data_as(C.c_void_p), w_.ctypes.data_as(C.c_void_p), _f32p(b_), M, N, K, int(gelu), _f32p(out)))
         return out
+
+    def test_gemm_perf(self, M: int, N: int, K: int, epi_kind: int, iters: int = 20) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.nb200_test_gemm_perf(self.h, M, N, K, epi_kind, iters, C.byref(ms)))
+        return ms.value
 
     def test_attention(self, qkv: np.ndarray, B: int, T: int, n_heads: int) -> np.ndarray:
         qkv = np.ascontiguousarray(qkv, np.float32)
