@@ -75,7 +75,8 @@ typedef enum {
     NB200_Q_MAX_BATCH = 4,
     NB200_Q_KERNEL_LAUNCHES = 5, /* kernels launched by this ctx since creation (monotonic) */
     NB200_Q_DEVICE_BYTES = 6,    /* device bytes owned by this ctx */
-    NB200_Q_COMPUTE_DTYPE = 7
+    NB200_Q_COMPUTE_DTYPE = 7,
+    NB200_Q_MAX_TARGET_POSITIONS = 8
 } nb200_query_key;
 
 /* kernel classes for the live per-kernel timers (bench.py roofline) */
@@ -149,6 +150,28 @@ NB200_API int nb200_reset_kv_cache(nb200_ctx *ctx);
  *      tokens (bounded tests). ----------------------------------------------------------------------------- */
 NB200_API int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
                         double *avg_logprob, double *no_speech_prob);
+
+/* the same loop at any temperature: t = 0 is nb200_decode_greedy; t > 0 replaces `softmax(p / t)` + `WeightedIndex::sample`
+ * (model.rs:340-348) by an inverse-CDF draw on the device from a counter-based generator seeded with `seed` (the reference
+ * seeds StdRng from entropy, monolingual.rs:439, so only the distribution is comparable). */
+NB200_API int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens, uint32_t *tokens_out,
+                           size_t *n_tokens, double *avg_logprob, double *no_speech_prob);
+
+/* ---- host side of norma's whisper `Model` (C++ mirror of model.rs:55-191): buffering, 30 s slicing,
+ *      temperature fallback, timestamp segmentation and seek.  ctx = NULL creates a model over a SCRIPTED backend whose
+ *      decoding results are pushed with nb200_model_script_push (host-logic tests without a GPU). ------------------- */
+typedef struct nb200_model nb200_model;
+NB200_API int nb200_model_create(nb200_ctx *ctx, const nb200_special_tokens *tok, size_t max_chunk_len, uint64_t seed, nb200_model **out);
+NB200_API void nb200_model_destroy(nb200_model *m);
+NB200_API const char *nb200_model_last_error(nb200_model *m);
+NB200_API int nb200_model_set_vocab(nb200_model *m, uint32_t id, const char *bytes, size_t n);
+/* replaces `Model::transcribe(&mut self, data: &mut Vec<f32>, final_chunk) -> Result<String, _>` (model.rs:55-160).
+ * text_out: NUL-terminated (truncated to text_cap); seg_out: [n_segments, len_0, tokens_0.., len_1, tokens_1.., ..] */
+NB200_API int nb200_model_transcribe(nb200_model *m, const float *data, size_t n, int final_chunk, char *text_out, size_t text_cap,
+                                     size_t *text_len, uint32_t *seg_out, size_t seg_cap, size_t *seg_len);
+NB200_API int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_encodes, size_t *n_decodes, size_t *n_resets);
+NB200_API int nb200_model_script_push(nb200_model *m, double avg_logprob, double no_speech_prob, const uint32_t *tokens, size_t n);
+NB200_API int nb200_model_script_log(nb200_model *m, size_t i, size_t *encode_len, double *decode_temp);
 
 /* ---- measurement helpers (bench.py): CUDA events on the ctx stream ------------------------------------ */
 NB200_API int nb200_timer_start(nb200_ctx *ctx);

@@ -430,6 +430,7 @@ int nb200_query(nb200_ctx *ctx, nb200_query_key key, int64_t *out) {
         case NB200_Q_KERNEL_LAUNCHES: *out = ctx->launches; break;
         case NB200_Q_DEVICE_BYTES: *out = (int64_t)ctx->device_bytes; break;
         case NB200_Q_COMPUTE_DTYPE: *out = ctx->compute; break;
+        case NB200_Q_MAX_TARGET_POSITIONS: *out = ctx->cfg.max_target_positions; break;
         default: return nb200_fail(ctx, NB200_INVALID_ARG, "query: unknown key %d", (int)key);
     }
     return NB200_OK;
@@ -761,7 +762,13 @@ int nb200_reset_kv_cache(nb200_ctx *ctx) {
 
 int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens, double *avg_logprob,
                         double *no_speech_prob) {
+    return nb200_decode(ctx, n_windows, 0.0f, 0, max_new_tokens, tokens_out, n_tokens, avg_logprob, no_speech_prob);
+}
+
+int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
+                 double *avg_logprob, double *no_speech_prob) {
     NB_TRY(check_decoder(ctx));
+    if (!(temperature >= 0.0f)) return nb200_fail(ctx, NB200_INVALID_ARG, "decode: temperature must be >= 0");
     const nb200_config &c = ctx->cfg;
     if (!ctx->has_tokens) return nb200_fail(ctx, NB200_NOT_LOADED, "special tokens not set (call nb200_set_tokens)");
     if (n_windows == 0 || (int)n_windows > ctx->n_resident || !tokens_out || !n_tokens)
@@ -775,7 +782,7 @@ int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens,
         NB_TRY(decoder_step(ctx, 0, B, pos, pos == 0 || pos == plen - 1));
         if (pos == 0) NB_TRY(decoder_nospeech(ctx, B));
     }
-    NB_TRY(decoder_select(ctx, B, (int)max_new_tokens));
+    NB_TRY(decoder_select(ctx, B, (int)max_new_tokens, temperature, seed));
     std::vector<int> done(B);
     for (int pos = plen; pos < P; ++pos) {
         CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -784,7 +791,7 @@ int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens,
         for (int b = 0; b < B; ++b) all &= done[b] != 0;
         if (all) break;
         NB_TRY(decoder_step(ctx, 0, B, pos, 1));
-        NB_TRY(decoder_select(ctx, B, (int)max_new_tokens));
+        NB_TRY(decoder_select(ctx, B, (int)max_new_tokens, temperature, seed));
     }
     std::vector<uint32_t> toks((size_t)B * P);
     std::vector<int> len(B);

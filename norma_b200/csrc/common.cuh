@@ -203,7 +203,7 @@ int simt_init(nb200_ctx *ctx);
 int gemm_tc_init(nb200_ctx *ctx);
 int attn_tc_init(nb200_ctx *ctx);
 int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);
-int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens);
+int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens, float temperature, unsigned long long seed);
 int decoder_nospeech(nb200_ctx *ctx, int n_windows);
 int decoder_init_state(nb200_ctx *ctx, int n_windows);
 // api.cu

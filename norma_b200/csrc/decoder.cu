@@ -227,6 +227,8 @@ struct SelectParams {
     int *len, *last_ts, *done, *nsampled;
     double *sumlp;
     int V, max_pos, max_new;
+    float temperature;          // 0: greedy arg-max; > 0: sample from softmax(p_masked / t)
+    unsigned long long seed;
     uint32_t eot, nts, ts_zero, ts_one;
 };
 
@@ -275,10 +277,7 @@ decode_select_kernel(SelectParams sp) {
             mode = (sum_ts >= max_text) ? 2 : 3;
         }
     }
-    // arg-max of the masked probabilities; among equal maxima the LAST index wins (Rust `max_by`)
-    float best = -INFINITY;
-    int best_i = -1;
-    for (int i = tid; i < V; i += 1024) {
+    auto masked_p = [&](int i) -> float {
         bool masked;
         if (mode == 0) masked = i < (int)sp.ts_zero || i > (int)sp.ts_one;
         else {
@@ -287,7 +286,69 @@ decode_select_kernel(SelectParams sp) {
             else if (mode == 2) masked |= i <= nts || i <= last_ts;
             else masked |= (i > nts && i <= last_ts);
         }
-        float p = masked ? -INFINITY : x[i] / sum;
+        return masked ? -INFINITY : x[i] / sum;
+    };
+    float best = -INFINITY;
+    int best_i = -1;
+    if (sp.temperature > 0.f) {
+        // model.rs:340-348: prs = softmax(p_masked / t); next = WeightedIndex(prs).sample(rng); all-NaN (everything masked) -> eot.
+        // Inverse CDF over contiguous per-thread ranges; the uniform comes from a counter-based hash of (seed, window, step).
+        __shared__ float s_part[1024];
+        __shared__ int s_pick;
+        const float inv_t = 1.0f / sp.temperature;
+        float pm = -INFINITY;
+        for (int i = tid; i < V; i += 1024) pm = fmaxf(pm, masked_p(i));
+        const float pmax = block_max(pm, red);
+        const int per = (V + 1023) / 1024, lo = tid * per, hi = min(V, lo + per);
+        float local = 0.f;
+        for (int i = lo; i < hi; ++i) local += expf((masked_p(i) - pmax) * inv_t);  // exp(-inf) = 0 for masked entries
+        s_part[tid] = local;
+        if (tid == 0) s_pick = -1;
+        __syncthreads();
+        if (tid == 0 && pmax > -INFINITY) {
+            float total = 0.f;
+            for (int t = 0; t < 1024; ++t) total += s_part[t];
+            unsigned long long z = sp.seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(b * 65536 + sp.nsampled[b] + 1);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;  // splitmix64
+            const float target = (float)(z >> 40) * (1.0f / 16777216.0f) * total;
+            float acc = 0.f;
+            int t = 0;
+            for (; t < 1023; ++t) {
+                if (acc + s_part[t] > target) break;
+                acc += s_part[t];
+            }
+            int pick = -1;
+            const int l2 = t * per, h2 = min(V, l2 + per);
+            for (int i = l2; i < h2; ++i) {
+                const float q = expf((masked_p(i) - pmax) * inv_t);
+                if (q > 0.f) pick = i;  // last candidate with mass: fallback against rounding at the range end
+                acc += q;
+                if (acc > target && q > 0.f) break;
+            }
+            s_pick = pick;
+        }
+        __syncthreads();
+        best_i = s_pick;
+        if (best_i >= 0) best = masked_p(best_i);
+        if (tid == 0 && best_i < 0) {  // every candidate masked: the reference pushes eot and stops (model.rs:343-346)
+            int l = len;
+            sp.tokens[(size_t)b * sp.max_pos + l] = sp.eot;
+            sp.len[b] = l + 1;
+            sp.done[b] = 1;
+        }
+        if (best_i < 0) return;
+        // fall through to the shared state update below with (best, best_i); skip the arg-max reduction
+        if (tid == 0) { red[0] = best; red_i[0] = best_i; }
+        for (int i = 1; i < 32; ++i)
+            if (tid == 0) { red[i] = -INFINITY; red_i[i] = -1; }
+        __syncthreads();
+        goto update_state;
+    }
+    // arg-max of the masked probabilities; among equal maxima the LAST index wins (Rust `max_by`)
+    for (int i = tid; i < V; i += 1024) {
+        float p = masked_p(i);
         if (p >= best) { best = p; best_i = i; }  // ascending i: >= keeps the last
     }
 #pragma unroll
@@ -299,7 +360,10 @@ decode_select_kernel(SelectParams sp) {
     __syncthreads();
     if ((tid & 31) == 0) { red[tid >> 5] = best; red_i[tid >> 5] = best_i; }
     __syncthreads();
+update_state:
     if (tid == 0) {
+        best = red[0];
+        best_i = red_i[0];
         for (int i = 1; i < 32; ++i)
             if (red[i] > best || (red[i] == best && red_i[i] > best_i)) { best = red[i]; best_i = red_i[i]; }
         const uint32_t next = (uint32_t)best_i;
@@ -494,12 +558,13 @@ int decoder_nospeech(nb200_ctx *ctx, int n_windows) {
     return NB200_OK;
 }
 
-int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens) {
+int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens, float temperature, unsigned long long seed) {
     KernelScope ks(ctx, NB200_K_DECODE_SELECT);
     SelectParams sp;
     sp.logits = ctx->logits; sp.suppress = ctx->suppress; sp.tokens = ctx->d_tokens;
     sp.len = ctx->d_len; sp.last_ts = ctx->d_last_ts; sp.done = ctx->d_done; sp.nsampled = ctx->d_nsampled; sp.sumlp = ctx->d_sumlp;
     sp.V = ctx->cfg.vocab_size; sp.max_pos = ctx->cfg.max_target_positions; sp.max_new = max_new_tokens;
+    sp.temperature = temperature; sp.seed = seed;
     sp.eot = ctx->tok.eot; sp.nts = ctx->tok.no_timestamps; sp.ts_zero = ctx->tok.ts_zero; sp.ts_one = ctx->tok.ts_one;
     decode_select_kernel<<<n_windows, 1024, 0, ctx->stream>>>(sp);
     CUDA_TRY(ctx, cudaGetLastError());

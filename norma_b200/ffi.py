@@ -16,7 +16,7 @@ NB200_OK = 0
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH"}
 DTYPES = {"f32": 0, "bf16": 1, "f16": 2, "f64": 3, "u8": 4, "u32": 5}
 KERNEL_CLASSES = ["mel", "mel_norm", "gemm", "attn", "layernorm", "decode_gemv", "decode_attn", "decode_select", "misc"]
-Q = dict(n_frames=0, enc_len=1, d_model=2, vocab=3, max_batch=4, kernel_launches=5, device_bytes=6, compute_dtype=7)
+Q = dict(n_frames=0, enc_len=1, d_model=2, vocab=3, max_batch=4, kernel_launches=5, device_bytes=6, compute_dtype=7, max_target_positions=8)
 
 # every symbol include/norma_b200.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
@@ -26,6 +26,8 @@ SYMBOLS = [
     "nb200_run_resident", "nb200_fetch_features", "nb200_fetch_mel", "nb200_decoder_forward", "nb200_final_linear",
     "nb200_reset_kv_cache", "nb200_decode_greedy", "nb200_timer_start", "nb200_timer_stop", "nb200_profile_enable",
     "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_gemm_perf", "nb200_test_attention",
+    "nb200_decode", "nb200_model_create", "nb200_model_destroy", "nb200_model_last_error", "nb200_model_set_vocab", "nb200_model_transcribe",
+    "nb200_model_state", "nb200_model_script_push", "nb200_model_script_log",
 ]
 
 
@@ -90,6 +92,15 @@ def load_library() -> C.CDLL:
         "nb200_test_gemm": ([p, p, p, f32p, i, i, i, i, f32p], i),
         "nb200_test_gemm_perf": ([p, i, i, i, i, i, f32p], i),
         "nb200_test_attention": ([p, f32p, i, i, i, f32p], i),
+        "nb200_decode": ([p, sz, C.c_float, C.c_uint64, sz, u32p, C.POINTER(sz), C.POINTER(C.c_double), C.POINTER(C.c_double)], i),
+        "nb200_model_create": ([p, C.POINTER(SpecialTokens), sz, C.c_uint64, C.POINTER(p)], i),
+        "nb200_model_destroy": ([p], None),
+        "nb200_model_last_error": ([p], C.c_char_p),
+        "nb200_model_set_vocab": ([p, C.c_uint32, C.c_char_p, sz], i),
+        "nb200_model_transcribe": ([p, f32p, sz, i, C.c_char_p, sz, C.POINTER(sz), u32p, sz, C.POINTER(sz)], i),
+        "nb200_model_state": ([p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)], i),
+        "nb200_model_script_push": ([p, C.c_double, C.c_double, u32p, sz], i),
+        "nb200_model_script_log": ([p, sz, C.POINTER(sz), C.POINTER(C.c_double)], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
@@ -270,6 +281,14 @@ class Context:
 
     def reset_kv_cache(self):
         self._ck(self.lib.nb200_reset_kv_cache(self.h))
+
+    def decode(self, n_windows: int = 1, temperature: float = 0.0, seed: int = 0, max_new_tokens: int = 0):
+        toks = np.zeros((n_windows, self.P), np.uint32)
+        n = (C.c_size_t * n_windows)()
+        alp = (C.c_double * n_windows)()
+        nsp = (C.c_double * n_windows)()
+        self._ck(self.lib.nb200_decode(self.h, n_windows, temperature, seed, max_new_tokens, toks.ctypes.data_as(C.POINTER(C.c_uint32)), n, alp, nsp))
+        return [dict(tokens=toks[b, : n[b]].tolist(), avg_logprob=alp[b], no_speech_prob=nsp[b]) for b in range(n_windows)]
 
     def decode_greedy(self, n_windows: int = 1, max_new_tokens: int = 0):
         toks = np.zeros((n_windows, self.P), np.uint32)

@@ -133,3 +133,27 @@ def synth_pcm(kind: str, seed: int, n: int = 480_000) -> np.ndarray:
 def synth_pcm_window(seed: int, n: int = 480_000) -> np.ndarray:
     """Config-3 mix (SURVEY §8 d): Gaussian / uniform / gated bursts by window index."""
     return synth_pcm(("gauss", "uniform", "bursts")[seed % 3], seed, n)
+
+
+def plant_decoder_plan(w: Dict[str, torch.Tensor], cfg: Dict[str, int], plan: Dict[int, int], seed: int = 7, pos_gain: float = 6.0,
+                       tok_gain: float = 2.0) -> Dict[str, torch.Tensor]:
+    """Make a random-init decoder CONFIDENT: after position p it predicts token plan[p] with probability ~1.
+
+    Random weights give near-uniform logits, so norma's `decode_with_fallback` always falls through to entropy-seeded
+    sampling.  Here the learned positional embedding of position p is a large vector along a random unit
+    direction u_p and the (tied) embedding of plan[p] is aligned with u_p, so the logit of plan[p] at position p
+    dominates; everything else stays random-init.  Tokens in `plan` must be distinct."""
+    assert len(set(plan.values())) == len(plan)
+    g = torch.Generator().manual_seed(seed)
+    d = cfg["d_model"]
+    w = dict(w)
+    pos = w["model.decoder.embed_positions.weight"].clone()
+    emb = w["model.decoder.embed_tokens.weight"].clone()
+    q, _ = torch.linalg.qr(torch.randn(d, len(plan) + 4, generator=g))
+    for k, (p, tok) in enumerate(sorted(plan.items())):
+        u = q[:, k]
+        pos[p] = pos_gain * u
+        emb[tok] = tok_gain * u
+    w["model.decoder.embed_positions.weight"] = pos
+    w["model.decoder.embed_tokens.weight"] = emb
+    return w

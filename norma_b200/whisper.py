@@ -1,0 +1,213 @@
+"""Host-side mirror of norma's public API for this path, over the C ABI (names as in the reference):
+
+  SelectedDevice                      /root/reference/src/models/mod.rs:38-55
+  CommonModelParams                   /root/reference/src/models/mod.rs:57-117
+  monolingual.ModelType / Definition  /root/reference/src/models/whisper/monolingual.rs:32-174
+  Model.transcribe(data, final_chunk) /root/reference/src/models/whisper/model.rs:55-160 (implemented in C++,
+                                      norma_b200/csrc/host/whisper_host.cc, reached through nb200_model_*)
+
+What is NOT mirrored (out of scope): hf-hub download, tokenizer.json parsing, the Transcriber thread and
+cpal capture.  `Definition.try_to_model` therefore takes the weights / filters / vocabulary from the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import ffi, filters, synth
+
+SAMPLE_RATE = 16_000
+MIN_CHUNK_LEN = 100       # models/mod.rs:59
+MIN_STRING_BUF_SIZE = 1   # models/mod.rs:63
+
+
+class WhisperError(Exception):
+    """whisper::Error (/root/reference/src/models/whisper/mod.rs:65-84)"""
+
+
+class Respnsivness(WhisperError):  # sic: the reference's spelling
+    def __init__(self):
+        super().__init__("The respnsivness must be over 1 second and under 30")
+
+
+@dataclass(frozen=True)
+class SelectedDevice:
+    kind: str = "cpu"
+    ordinal: int = 0
+
+    @staticmethod
+    def Cpu():
+        return SelectedDevice("cpu")
+
+    @staticmethod
+    def Cuda(n: int):
+        return SelectedDevice("cuda", n)
+
+    @staticmethod
+    def Metal():
+        return SelectedDevice("metal")
+
+
+class CommonModelParams:
+    def __init__(self, max_chunk_len: int, data_buffer_size: int, string_buffer_size: int):
+        self._max_chunk_len = max(max_chunk_len, MIN_CHUNK_LEN)
+        self._data_buffer_size = data_buffer_size + 2          # thingbuf's usable capacity is n - 2 (models/mod.rs:81)
+        self._string_buffer_size = max(string_buffer_size, MIN_STRING_BUF_SIZE)
+
+    def max_chunk_len(self) -> int:
+        return max(self._max_chunk_len, MIN_CHUNK_LEN)
+
+    def data_buffer_size(self) -> int:
+        return self._data_buffer_size
+
+    def string_buffer_size(self) -> int:
+        return self._string_buffer_size
+
+    def set_max_chunk_len(self, n: int):
+        self._max_chunk_len = max(n, MIN_CHUNK_LEN)
+
+    def set_data_buffer_size(self, n: int):
+        self._data_buffer_size = n + 2
+
+    def set_string_buffer_size(self, n: int):
+        self._string_buffer_size = max(n, MIN_STRING_BUF_SIZE)
+
+
+class ModelType(enum.Enum):
+    """monolingual::ModelType (monolingual.rs:32-111): (hub id, revision, architecture shape, vocab version)"""
+    QuantizedTinyEn = ("lmz/candle-whisper", "main", "tiny.en", "EnV1")
+    TinyEn = ("openai/whisper-tiny.en", "refs/pr/15", "tiny.en", "EnV1")
+    BaseEn = ("openai/whisper-base.en", "refs/pr/13", "base.en", "EnV1")
+    SmallEn = ("openai/whisper-small.en", "refs/pr/10", "small.en", "EnV1")
+    MediumEn = ("openai/whisper-medium.en", "main", "medium.en", "EnV1")
+    DistilMediumEn = ("distil-whisper/distil-medium.en", "main", "distil-medium.en", "V1")
+    DistilLargeEnV2 = ("distil-whisper/distil-large-v2", "main", "distil-large-v2", "V1")
+    DistilLargeEnV3 = ("distil-whisper/distil-large-v3", "main", "distil-large-v3", "V2")
+
+    @classmethod
+    def default(cls):
+        return cls.DistilLargeEnV3  # #[default], monolingual.rs:40-41
+
+    def id(self) -> str:
+        return self.value[0]
+
+    def rev(self) -> str:
+        return self.value[1]
+
+    def shape(self) -> str:
+        return self.value[2]
+
+    def vocab_version(self) -> str:
+        return self.value[3]
+
+    def quantized_ext(self) -> Optional[str]:
+        return "tiny-en" if self is ModelType.QuantizedTinyEn else None
+
+
+class Definition:
+    """monolingual::Definition (monolingual.rs:116-174)"""
+
+    def __init__(self, model: ModelType, device: SelectedDevice):
+        self.model, self.device = model, device
+        self.common_params = CommonModelParams(SAMPLE_RATE * 25, 3, 3)  # monolingual.rs:128
+
+    @staticmethod
+    def new(model: ModelType, device: SelectedDevice) -> "Definition":
+        return Definition(model, device)
+
+    def set_responsiveness(self, period_ms: int):
+        if 1_000 <= period_ms <= 30_000:  # monolingual.rs:147-156
+            self.common_params.set_max_chunk_len((SAMPLE_RATE * period_ms) // 1000)
+        else:
+            raise Respnsivness()
+
+    def set_data_buffer_size(self, size: int):
+        self.common_params.set_data_buffer_size(size)
+
+    def set_string_buffer_size(self, size: int):
+        self.common_params.set_string_buffer_size(size)
+
+    def blocking_try_to_model(self, weights: Dict[str, object], compute: str = "bf16", vocab: Optional[Dict[int, bytes]] = None,
+                              suppress_tokens: Sequence[int] = (), seed: int = 0) -> "Model":
+        """monolingual.rs:320-451 minus the hub download: the caller supplies what the reference reads from the hub."""
+        if self.device.kind != "cuda":
+            raise WhisperError("this build only implements SelectedDevice::Cuda(ord) (sm_100a, no CPU fallback)")
+        if self.model.quantized_ext() is not None:
+            raise WhisperError("quantized (q8_0) checkpoints are out of scope for the B200 path")
+        cfg = synth.model_config(self.model.shape())
+        ctx = ffi.Context(cfg, ordinal=self.device.ordinal, compute=compute, max_batch=1)
+        ctx.set_mel_filters(filters.mel_filters(cfg["num_mel_bins"]))  # Error::MelBins for anything but 80 | 128
+        ctx.load_weights(weights)
+        tok = synth.special_tokens(cfg["vocab_size"])
+        ctx.set_tokens(**tok)
+        ctx.set_suppress(suppress_tokens)
+        return Model(ctx, tok, self.common_params.max_chunk_len(), vocab, seed)
+
+
+class Model:
+    """whisper::Model (model.rs:16-160): `Data = f32`, `SAMPLE_RATE = 16_000`."""
+    SAMPLE_RATE = SAMPLE_RATE
+
+    def __init__(self, ctx: Optional[ffi.Context], tok: Dict[str, int], max_chunk_len: int, vocab: Optional[Dict[int, bytes]] = None,
+                 seed: int = 0):
+        self.lib = ffi.load_library()
+        self.ctx = ctx
+        t = ffi.SpecialTokens(tok["sot"], tok["eot"], tok["task"], 0xFFFFFFFF if tok.get("lang") is None else tok["lang"], tok["no_speech"],
+                              tok["no_timestamps"], tok["ts_zero"], tok["ts_one"])
+        h = C.c_void_p()
+        st = self.lib.nb200_model_create(ctx.h if ctx is not None else None, C.byref(t), max_chunk_len, seed, C.byref(h))
+        if st != 0:
+            raise ffi.Nb200Error(st, "nb200_model_create failed")
+        self.h = h
+        for i, b in (vocab or {}).items():
+            self.lib.nb200_model_set_vocab(self.h, i, b, len(b))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nb200_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transcribe(self, data: np.ndarray, final_chunk: bool) -> Tuple[str, List[List[int]]]:
+        """-> (text, emitted token segments).  `data` is consumed, as the reference's `&mut Vec<f32>` is."""
+        d = np.ascontiguousarray(data, np.float32)
+        text = C.create_string_buffer(1 << 16)
+        tl, sl = C.c_size_t(), C.c_size_t()
+        seg = np.zeros(1 << 14, np.uint32)
+        ptr = d.ctypes.data_as(C.POINTER(C.c_float)) if d.size else None
+        st = self.lib.nb200_model_transcribe(self.h, ptr, d.size, int(final_chunk), text, len(text), C.byref(tl),
+                                             seg.ctypes.data_as(C.POINTER(C.c_uint32)), seg.size, C.byref(sl))
+        if st != 0:
+            raise ffi.Nb200Error(st, (self.lib.nb200_model_last_error(self.h) or b"").decode())
+        segs, i = [], 1
+        for _ in range(int(seg[0])):
+            n = int(seg[i])
+            segs.append(seg[i + 1 : i + 1 + n].tolist())
+            i += 1 + n
+        return text.value.decode("utf-8", "replace"), segs
+
+    def state(self) -> Dict[str, int]:
+        a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self.lib.nb200_model_state(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return dict(buffered=a.value, n_encodes=b.value, n_decodes=c.value, n_resets=d.value)
+
+    # scripted backend (ctx is None): canned results for the host-logic tests
+    def script_push(self, tokens: Sequence[int], avg_logprob: float, no_speech_prob: float):
+        t = np.ascontiguousarray(np.asarray(list(tokens), np.uint32))
+        st = self.lib.nb200_model_script_push(self.h, avg_logprob, no_speech_prob, t.ctypes.data_as(C.POINTER(C.c_uint32)), t.size)
+        if st != 0:
+            raise ffi.Nb200Error(st, "script_push on a non-scripted model")
+
+    def script_log(self, i: int) -> Tuple[int, float]:
+        n, t = C.c_size_t(), C.c_double()
+        self.lib.nb200_model_script_log(self.h, i, C.byref(n), C.byref(t))
+        return (-1 if n.value == 2**64 - 1 else n.value), t.value
