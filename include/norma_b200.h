@@ -188,6 +188,8 @@ NB200_API int nb200_test_gemm(nb200_ctx *ctx, const void *a, const void *w, cons
 /* GEMM microbenchmark on zero-filled device buffers: epi_kind 0 = bias -> bf16, 1 = bias + GELU -> bf16,
  * 2 = bias + f32 residual in place -> f32; returns the average ms per launch over `iters` launches */
 NB200_API int nb200_test_gemm_perf(nb200_ctx *ctx, int M, int N, int K, int epi_kind, int iters, float *ms_out);
+/* tcgen05 attention microbenchmark: average ms per launch over `iters` launches on the given q|k|v */
+NB200_API int nb200_test_attention_perf(nb200_ctx *ctx, const float *qkv, int B, int T, int n_heads, int iters, float *ms_out);
 /* attention self-test: qkv host f32 [B*T][3*d] (q|k|v), h heads of 64 -> ctx_out [B*T][d] f32 */
 NB200_API int nb200_test_attention(nb200_ctx *ctx, const float *qkv, int B, int T, int n_heads, float *ctx_out);
 

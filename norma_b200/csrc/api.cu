@@ -370,6 +370,7 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
         NB_TRY(dev_alloc_t(ctx, (size_t)nm * 16, &ctx->filt_vals, true));
         NB_TRY(dev_alloc_t(ctx, nm, &ctx->filt_start, true));
         NB_TRY(dev_alloc_t(ctx, nm, &ctx->filt_len, true));
+        NB_TRY(dev_alloc_t(ctx, nm, &ctx->mel_slot_len, true));
         NB_TRY(dev_alloc_t(ctx, 1280, &ctx->mel_tables, true));
         NB_TRY(dev_alloc_t(ctx, B * N_SAMPLES, &ctx->pcm, true));
         NB_TRY(dev_alloc_t(ctx, B, &ctx->pcm_len, true));
@@ -957,6 +958,33 @@ int nb200_test_gemm_perf(nb200_ctx *ctx, int M, int N, int K, int epi_kind, int 
         return NB200_OK;
     }();
     cudaFree(dA); cudaFree(dW); cudaFree(dB); cudaFree(dC);
+    return st;
+}
+
+int nb200_test_attention_perf(nb200_ctx *ctx, const float *qkv, int B, int T, int n_heads, int iters, float *ms_out) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (ctx->compute != NB200_BF16 || !qkv || !ms_out || iters < 1) return nb200_fail(ctx, NB200_INVALID_ARG, "test_attention_perf: bf16 ctx required");
+    const int d = n_heads * HEAD_DIM;
+    const size_t nq = (size_t)B * T * 3 * d, no = (size_t)B * T * d;
+    float *dq32 = nullptr;
+    bf16 *dq16 = nullptr, *do16 = nullptr;
+    int st = [&]() -> int {
+        CUDA_TRY(ctx, cudaMalloc(&dq32, nq * 4));
+        CUDA_TRY(ctx, cudaMalloc(&dq16, nq * 2));
+        CUDA_TRY(ctx, cudaMalloc(&do16, no * 2));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dq32, qkv, nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+        NB_TRY(launch_f32_to_bf16(ctx, dq32, dq16, nq));
+        for (int i = 0; i < 3; ++i) NB_TRY(launch_attention_tc(ctx, dq16, do16, B, T, n_heads));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+        for (int i = 0; i < iters; ++i) NB_TRY(launch_attention_tc(ctx, dq16, do16, B, T, n_heads));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stop, ctx->stream));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+        *ms_out = ms / iters;
+        return NB200_OK;
+    }();
+    cudaFree(dq32); cudaFree(dq16); cudaFree(do16);
     return st;
 }
 

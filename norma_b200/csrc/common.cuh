@@ -95,7 +95,8 @@ struct nb200_ctx {
     // mel
     float *filt_vals = nullptr;  // banded filterbank: [n_mel][MEL_BAND] values
     int *filt_start = nullptr;   // [n_mel] first non-zero bin
-    int *filt_len = nullptr;
+    int *filt_len = nullptr;     // [n_mel] mel row of slot entry e (slot-ordered filterbank, see mel_setup_filters)
+    int *mel_slot_len = nullptr; // [n_mel / 8] warp-uniform trip count per slot
     float *mel_tables = nullptr;  // hann[400] | tw200[8*25*2] | tw400[201*2]
     float *pcm = nullptr;         // [max_batch][N_SAMPLES]
     int *pcm_len = nullptr;       // [max_batch]

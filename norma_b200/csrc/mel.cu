@@ -13,6 +13,8 @@
 
 #include <math.h>
 
+#include <algorithm>
+
 namespace {
 
 constexpr int FR_PER_CTA = 32;
@@ -76,10 +78,13 @@ __global__ void mel_init_max_kernel(unsigned *mel_max, int n) {
     if (i < n) mel_max[i] = enc_max(-10.0f);  // the zero-pad frames candle appends are exactly log10(1e-10)
 }
 
+// Persistent: each CTA loops over (window, 32-frame tile) work items; tables and filters are staged once per CTA, and the
+// samples of the NEXT tile are prefetched into registers while the current tile is transformed.
 __global__ void __launch_bounds__(MEL_THREADS, 2)
 mel_kernel(const float *__restrict__ pcm, const int *__restrict__ pcm_len, const float *__restrict__ tables,
-           const float *__restrict__ filt_vals, const int *__restrict__ filt_start,
-           const int *__restrict__ filt_len, int n_mel, float *__restrict__ logmel, unsigned *__restrict__ mel_max) {
+           const float *__restrict__ filt_vals, const int *__restrict__ filt_start, const int *__restrict__ filt_row,
+           const int *__restrict__ slot_len, int n_mel, int n_tiles, int tiles_per_window, float *__restrict__ logmel,
+           unsigned *__restrict__ mel_max) {
     extern __shared__ __align__(16) float smem[];
     float *s_pcm = smem;                                  // PCM_SMEM (aliased by s_out after the FFT loads)
     float *s_out = smem;                                  // [n_mel][OUT_STRIDE]
@@ -88,18 +93,15 @@ mel_kernel(const float *__restrict__ pcm, const int *__restrict__ pcm_len, const
     float *s_hann = s_pow + FR_PER_CTA * POW_STRIDE;      // [400]
     float2 *s_tw200 = (float2 *)(s_hann + 400);           // [25][8]
     float2 *s_tw400 = s_tw200 + 200;                      // [201] (+1 pad)
-    float *s_fv = (float *)(s_tw400 + 202);               // [n_mel][BAND_STRIDE]
+    float *s_fv = (float *)(s_tw400 + 202);               // [n_mel][BAND_STRIDE]  (slot-major: entry s*8 + lane)
     int *s_fstart = (int *)(s_fv + n_mel * BAND_STRIDE);  // [n_mel]
-    int *s_flen = s_fstart + n_mel;
+    int *s_frow = s_fstart + n_mel;                       // [n_mel]
+    int *s_slen = s_frow + n_mel;                         // [n_mel / 8]
     __shared__ float s_wmax[MEL_THREADS / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    const int f0 = blockIdx.x * FR_PER_CTA;
-    const int len = pcm_len[b];
-    const float *wpcm = pcm + (size_t)b * N_SAMPLES;
 
-    // ---- stage tables, filters and this CTA's samples ------------------------------------------------------
+    // ---- once per CTA: tables and the slot-ordered banded filterbank ----------------------------------------
     for (int i = tid; i < 400; i += MEL_THREADS) s_hann[i] = tables[i];
     for (int i = tid; i < 400; i += MEL_THREADS) ((float *)s_tw200)[i] = tables[400 + i];
     for (int i = tid; i < 402; i += MEL_THREADS) ((float *)s_tw400)[i] = tables[800 + i];
@@ -107,156 +109,185 @@ mel_kernel(const float *__restrict__ pcm, const int *__restrict__ pcm_len, const
         s_fv[(i / MEL_BAND) * BAND_STRIDE + (i % MEL_BAND)] = filt_vals[i];
     for (int i = tid; i < n_mel; i += MEL_THREADS) {
         s_fstart[i] = filt_start[i];
-        s_flen[i] = filt_len[i];
+        s_frow[i] = filt_row[i];
     }
-    const int s_base = f0 * HOP;  // first sample of the CTA
-    constexpr int N_S = (FR_PER_CTA - 1) * HOP + N_FFT;  // 5360 samples, multiple of 4
-    for (int i = tid * 4; i < N_S; i += MEL_THREADS * 4) {
-        int g = s_base + i;
-        float4 v;
-        if (g + 3 < len) {
-            v = __ldg((const float4 *)(wpcm + g));
-        } else {
-            v.x = g + 0 < len ? __ldg(wpcm + g + 0) : 0.f;
-            v.y = g + 1 < len ? __ldg(wpcm + g + 1) : 0.f;
-            v.z = g + 2 < len ? __ldg(wpcm + g + 2) : 0.f;
-            v.w = g + 3 < len ? __ldg(wpcm + g + 3) : 0.f;
-        }
-        *(float4 *)(s_pcm + pcm_idx(i)) = v;
-    }
-    __syncthreads();
+    for (int i = tid; i < n_mel / 8; i += MEL_THREADS) s_slen[i] = slot_len[i];
 
-    // ---- per-lane 25-point DFT over n1 (element n1 of lane n2 is z[8*n1 + n2]) -----------------------------
+    constexpr int N_S = (FR_PER_CTA - 1) * HOP + N_FFT;  // 5360 samples = 1340 float4
+    constexpr int N_V4 = N_S / 4;
+    constexpr int PF = (N_V4 + MEL_THREADS - 1) / MEL_THREADS;  // float4 registers per thread
+    float4 pf[PF];
+    auto prefetch = [&](int tile) {
+        const int b = tile / tiles_per_window, f0 = (tile - b * tiles_per_window) * FR_PER_CTA;
+        const int len = pcm_len[b];
+        const float *wpcm = pcm + (size_t)b * N_SAMPLES;
+        const int s_base = f0 * HOP;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int i = (tid + u * MEL_THREADS) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < N_S) {
+                const int g = s_base + i;
+                if (g + 3 < len) v = __ldg((const float4 *)(wpcm + g));
+                else {
+                    if (g + 0 < len) v.x = __ldg(wpcm + g + 0);
+                    if (g + 1 < len) v.y = __ldg(wpcm + g + 1);
+                    if (g + 2 < len) v.z = __ldg(wpcm + g + 2);
+                    if (g + 3 < len) v.w = __ldg(wpcm + g + 3);
+                }
+            }
+            pf[u] = v;
+        }
+    };
+    int tile = blockIdx.x;
+    if (tile < n_tiles) prefetch(tile);
+
     const int n2 = lane & 7, grp = lane >> 3;
     const int fi = warp * 4 + grp;
-    float zr[25], zi[25];
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_window, f0 = (tile - b * tiles_per_window) * FR_PER_CTA;
+        __syncthreads();  // previous tile's output store no longer reads s_out (aliases s_pcm); tables visible on the first pass
 #pragma unroll
-    for (int n1 = 0; n1 < 25; ++n1) {
-        int s = fi * HOP + 16 * n1 + 2 * n2;
-        float2 v = *(const float2 *)(s_pcm + pcm_idx(s));
-        float2 hw = *(const float2 *)(s_hann + 16 * n1 + 2 * n2);
-        zr[n1] = v.x * hw.x;
-        zi[n1] = v.y * hw.y;
-    }
-    // n1 = 5a + b: DFT over a for each b (stride 5), twiddle W25^(b*c), DFT over b for each c (stride 1)
-#pragma unroll
-    for (int bb = 0; bb < 5; ++bb) dft5<5>(zr + bb, zi + bb);  // now index 5c + b holds Y_b[c]
-#pragma unroll
-    for (int c = 1; c < 5; ++c) {
-#pragma unroll
-        for (int bb = 1; bb < 5; ++bb) {
-            float wr = W25R[bb * c], wi = W25I[bb * c];
-            float xr = zr[5 * c + bb], xi = zi[5 * c + bb];
-            zr[5 * c + bb] = xr * wr - xi * wi;
-            zi[5 * c + bb] = xr * wi + xi * wr;
+        for (int u = 0; u < PF; ++u) {
+            const int i = (tid + u * MEL_THREADS) * 4;
+            if (i < N_S) *(float4 *)(s_pcm + pcm_idx(i)) = pf[u];
         }
-    }
-#pragma unroll
-    for (int c = 0; c < 5; ++c) dft5<1>(zr + 5 * c, zi + 5 * c);  // index 5c + e holds X[c + 5e]
-    // reorder to k1 order and apply the 200-point twiddle W200^(n2*k1)
-    float yr[25], yi[25];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-#pragma unroll
-        for (int e = 0; e < 5; ++e) {
-            const int k1 = c + 5 * e;
-            float2 w = s_tw200[k1 * 8 + n2];
-            float xr = zr[5 * c + e], xi = zi[5 * c + e];
-            yr[k1] = xr * w.x - xi * w.y;
-            yi[k1] = xr * w.y + xi * w.x;
-        }
-    }
-    // ---- radix-8 across the 8 lanes (DIF; lane n2 ends up holding k2 = bitrev3(n2)) ------------------------
-    {
-        const float R = 0.70710678118654752f;
-        const int j = n2 & 3;
-        const bool up4 = n2 & 4, up2 = n2 & 2, up1 = n2 & 1;
-        // W8^j for the upper half of stage 1, identity otherwise
-        float w1r = !up4 ? 1.f : (j == 0 ? 1.f : (j == 1 ? R : (j == 2 ? 0.f : -R)));
-        float w1i = !up4 ? 0.f : (j == 0 ? 0.f : (j == 1 ? -R : (j == 2 ? -1.f : -R)));
-        const float s4 = up4 ? -1.f : 1.f, s2 = up2 ? -1.f : 1.f, s1 = up1 ? -1.f : 1.f;
-        const bool rot2 = up2 && (n2 & 1);  // multiply by W4^1 = -i
-#pragma unroll
-        for (int k = 0; k < 25; ++k) {
-            float pr = __shfl_xor_sync(0xffffffffu, yr[k], 4), pi = __shfl_xor_sync(0xffffffffu, yi[k], 4);
-            float tr = pr + s4 * yr[k], ti = pi + s4 * yi[k];
-            float ar = tr * w1r - ti * w1i, ai = tr * w1i + ti * w1r;
-            pr = __shfl_xor_sync(0xffffffffu, ar, 2);
-            pi = __shfl_xor_sync(0xffffffffu, ai, 2);
-            tr = pr + s2 * ar;
-            ti = pi + s2 * ai;
-            ar = rot2 ? ti : tr;
-            ai = rot2 ? -tr : ti;
-            pr = __shfl_xor_sync(0xffffffffu, ar, 1);
-            pi = __shfl_xor_sync(0xffffffffu, ai, 1);
-            yr[k] = pr + s1 * ar;
-            yi[k] = pi + s1 * ai;
-        }
-    }
-    // ---- real-FFT post-processing + power ---------------------------------------------------------------
-    {
-        const int k2 = ((n2 & 1) << 2) | (n2 & 2) | ((n2 & 4) >> 2);
-        const int pk2 = (8 - k2) & 7;
-        const int src0 = (lane & ~7) | (((pk2 & 1) << 2) | (pk2 & 2) | ((pk2 & 4) >> 2));
-        float *prow = s_pow + fi * POW_STRIDE;
-#pragma unroll
-        for (int k1 = 0; k1 < 25; ++k1) {
-            float qr, qi;
-            if (k1 == 0) {
-                qr = __shfl_sync(0xffffffffu, yr[0], src0);
-                qi = __shfl_sync(0xffffffffu, yi[0], src0);
-            } else {
-                qr = __shfl_xor_sync(0xffffffffu, yr[25 - k1], 7);
-                qi = __shfl_xor_sync(0xffffffffu, yi[25 - k1], 7);
-            }
-            const int k = k1 + 25 * k2;
-            float er = 0.5f * (yr[k1] + qr), ei = 0.5f * (yi[k1] - qi);
-            float orr = 0.5f * (yi[k1] + qi), oi = -0.5f * (yr[k1] - qr);
-            float2 w = s_tw400[k];
-            float xr = er + w.x * orr - w.y * oi;
-            float xi = ei + w.x * oi + w.y * orr;
-            float p = xr * xr + xi * xi;
-            prow[k] = (k == 0) ? p : 2.0f * p;  // candle: p[j] += p[400-j] for j = 1..199
-            if (k1 == 0 && k2 == 0) {
-                float x200 = yr[0] - yi[0];
-                prow[200] = x200 * x200;
-            }
-        }
-    }
-    __syncthreads();  // all warps done reading s_pcm (aliased by s_out); power rows visible
+        __syncthreads();
+        if (tile + (int)gridDim.x < n_tiles) prefetch(tile + gridDim.x);  // in flight while this tile is transformed
 
-    // ---- banded mel projection, log10, running max ----------------------------------------------------------
-    float vmax = -10.0f;
-    {
-        const float *prow = s_pow + fi * POW_STRIDE;
-        const bool valid = (f0 + fi) < N_FRAMES;
-        for (int m = n2; m < n_mel; m += 8) {
-            const int st = s_fstart[m], ln = s_flen[m];
-            const float *fv = s_fv + m * BAND_STRIDE;
-            float sum = 0.f;
-            for (int j = 0; j < ln; ++j) sum += prow[st + j] * fv[j];
-            float v = log10f(fmaxf(sum, 1e-10f));
-            s_out[m * OUT_STRIDE + fi] = v;
-            if (valid) vmax = fmaxf(vmax, v);
-        }
-    }
+        // ---- per-lane 25-point DFT over n1 (element n1 of lane n2 is z[8*n1 + n2]) -----------------------------
+        float zr[25], zi[25];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane == 0) s_wmax[warp] = vmax;
-    __syncthreads();
-    if (tid == 0) {
-        float m = s_wmax[0];
-        for (int i = 1; i < MEL_THREADS / 32; ++i) m = fmaxf(m, s_wmax[i]);
-        atomicMax(mel_max + b, enc_max(m));
-    }
-    // ---- coalesced store: rows of 32 frames = 128 B ---------------------------------------------------------
-    float *obase = logmel + (size_t)b * n_mel * N_FRAMES;
-    for (int i = tid; i < n_mel * (FR_PER_CTA / 4); i += MEL_THREADS) {
-        int m = i >> 3, seg = (i & 7) * 4;
-        int f = f0 + seg;
-        if (f < N_FRAMES) {
-            float4 v = *(const float4 *)(s_out + m * OUT_STRIDE + seg);
-            *(float4 *)(obase + (size_t)m * N_FRAMES + f) = v;
+        for (int n1 = 0; n1 < 25; ++n1) {
+            int sidx = fi * HOP + 16 * n1 + 2 * n2;
+            float2 v = *(const float2 *)(s_pcm + pcm_idx(sidx));
+            float2 hw = *(const float2 *)(s_hann + 16 * n1 + 2 * n2);
+            zr[n1] = v.x * hw.x;
+            zi[n1] = v.y * hw.y;
+        }
+        // n1 = 5a + b: DFT over a for each b (stride 5), twiddle W25^(b*c), DFT over b for each c (stride 1)
+#pragma unroll
+        for (int bb = 0; bb < 5; ++bb) dft5<5>(zr + bb, zi + bb);  // now index 5c + b holds Y_b[c]
+#pragma unroll
+        for (int c = 1; c < 5; ++c) {
+#pragma unroll
+            for (int bb = 1; bb < 5; ++bb) {
+                float wr = W25R[bb * c], wi = W25I[bb * c];
+                float xr = zr[5 * c + bb], xi = zi[5 * c + bb];
+                zr[5 * c + bb] = xr * wr - xi * wi;
+                zi[5 * c + bb] = xr * wi + xi * wr;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) dft5<1>(zr + 5 * c, zi + 5 * c);  // index 5c + e holds X[c + 5e]
+        // reorder to k1 order and apply the 200-point twiddle W200^(n2*k1)
+        float yr[25], yi[25];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                const int k1 = c + 5 * e;
+                float2 w = s_tw200[k1 * 8 + n2];
+                float xr = zr[5 * c + e], xi = zi[5 * c + e];
+                yr[k1] = xr * w.x - xi * w.y;
+                yi[k1] = xr * w.y + xi * w.x;
+            }
+        }
+        // ---- radix-8 across the 8 lanes (DIF; lane n2 ends up holding k2 = bitrev3(n2)) ------------------------
+        {
+            const float R = 0.70710678118654752f;
+            const int j = n2 & 3;
+            const bool up4 = n2 & 4, up2 = n2 & 2, up1 = n2 & 1;
+            // W8^j for the upper half of stage 1, identity otherwise
+            float w1r = !up4 ? 1.f : (j == 0 ? 1.f : (j == 1 ? R : (j == 2 ? 0.f : -R)));
+            float w1i = !up4 ? 0.f : (j == 0 ? 0.f : (j == 1 ? -R : (j == 2 ? -1.f : -R)));
+            const float s4 = up4 ? -1.f : 1.f, s2 = up2 ? -1.f : 1.f, s1 = up1 ? -1.f : 1.f;
+            const bool rot2 = up2 && (n2 & 1);  // multiply by W4^1 = -i
+#pragma unroll
+            for (int k = 0; k < 25; ++k) {
+                float pr = __shfl_xor_sync(0xffffffffu, yr[k], 4), pi = __shfl_xor_sync(0xffffffffu, yi[k], 4);
+                float tr = pr + s4 * yr[k], ti = pi + s4 * yi[k];
+                float ar = tr * w1r - ti * w1i, ai = tr * w1i + ti * w1r;
+                pr = __shfl_xor_sync(0xffffffffu, ar, 2);
+                pi = __shfl_xor_sync(0xffffffffu, ai, 2);
+                tr = pr + s2 * ar;
+                ti = pi + s2 * ai;
+                ar = rot2 ? ti : tr;
+                ai = rot2 ? -tr : ti;
+                pr = __shfl_xor_sync(0xffffffffu, ar, 1);
+                pi = __shfl_xor_sync(0xffffffffu, ai, 1);
+                yr[k] = pr + s1 * ar;
+                yi[k] = pi + s1 * ai;
+            }
+        }
+        // ---- real-FFT post-processing + power ---------------------------------------------------------------
+        {
+            const int k2 = ((n2 & 1) << 2) | (n2 & 2) | ((n2 & 4) >> 2);
+            const int pk2 = (8 - k2) & 7;
+            const int src0 = (lane & ~7) | (((pk2 & 1) << 2) | (pk2 & 2) | ((pk2 & 4) >> 2));
+            float *prow = s_pow + fi * POW_STRIDE;
+#pragma unroll
+            for (int k1 = 0; k1 < 25; ++k1) {
+                float qr, qi;
+                if (k1 == 0) {
+                    qr = __shfl_sync(0xffffffffu, yr[0], src0);
+                    qi = __shfl_sync(0xffffffffu, yi[0], src0);
+                } else {
+                    qr = __shfl_xor_sync(0xffffffffu, yr[25 - k1], 7);
+                    qi = __shfl_xor_sync(0xffffffffu, yi[25 - k1], 7);
+                }
+                const int k = k1 + 25 * k2;
+                float er = 0.5f * (yr[k1] + qr), ei = 0.5f * (yi[k1] - qi);
+                float orr = 0.5f * (yi[k1] + qi), oi = -0.5f * (yr[k1] - qr);
+                float2 w = s_tw400[k];
+                float xr = er + w.x * orr - w.y * oi;
+                float xi = ei + w.x * oi + w.y * orr;
+                float p = xr * xr + xi * xi;
+                prow[k] = (k == 0) ? p : 2.0f * p;  // candle: p[j] += p[400-j] for j = 1..199
+                if (k1 == 0 && k2 == 0) {
+                    float x200 = yr[0] - yi[0];
+                    prow[200] = x200 * x200;
+                }
+            }
+        }
+        __syncthreads();  // all warps done reading s_pcm (aliased by s_out); power rows visible
+
+        // ---- banded mel projection (slot-ordered: the 8 lanes of a slot share one trip count), log10, running max ---
+        float vmax = -10.0f;
+        {
+            const float *prow = s_pow + fi * POW_STRIDE;
+            const bool valid = (f0 + fi) < N_FRAMES;
+            const int n_slots = n_mel >> 3;
+            for (int sl = 0; sl < n_slots; ++sl) {
+                const int e = sl * 8 + n2;
+                const int st = s_fstart[e], ln = s_slen[sl];  // ln is warp-uniform
+                const float *fv = s_fv + e * BAND_STRIDE;
+                float sum = 0.f;
+                for (int j = 0; j < ln; ++j) sum = fmaf(prow[st + j], fv[j], sum);
+                // log10(x) = log2(x) * log10(2); lg2.approx is within 2^-22 absolute on this range (1e-7 after /4)
+                float v = __log2f(fmaxf(sum, 1e-10f)) * 0.30102999566398120f;
+                s_out[s_frow[e] * OUT_STRIDE + fi] = v;
+                if (valid) vmax = fmaxf(vmax, v);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0) s_wmax[warp] = vmax;
+        __syncthreads();
+        if (tid == 0) {
+            float m = s_wmax[0];
+            for (int i = 1; i < MEL_THREADS / 32; ++i) m = fmaxf(m, s_wmax[i]);
+            atomicMax(mel_max + b, enc_max(m));
+        }
+        // ---- coalesced store: rows of 32 frames = 128 B ---------------------------------------------------------
+        float *obase = logmel + (size_t)b * n_mel * N_FRAMES;
+        for (int i = tid; i < n_mel * (FR_PER_CTA / 4); i += MEL_THREADS) {
+            int m = i >> 3, seg = (i & 7) * 4;
+            int f = f0 + seg;
+            if (f < N_FRAMES) {
+                float4 v = *(const float4 *)(s_out + m * OUT_STRIDE + seg);
+                *(float4 *)(obase + (size_t)m * N_FRAMES + f) = v;
+            }
         }
     }
 }
@@ -297,7 +328,7 @@ __global__ void mel_norm_kernel(const float *__restrict__ in, const unsigned *__
 
 static size_t mel_smem_bytes(int n_mel) {
     size_t a = (PCM_SMEM > n_mel * OUT_STRIDE) ? PCM_SMEM : n_mel * OUT_STRIDE;
-    size_t fl = a + FR_PER_CTA * POW_STRIDE + 400 + 400 + 404 + (size_t)n_mel * BAND_STRIDE + 2 * n_mel;
+    size_t fl = a + FR_PER_CTA * POW_STRIDE + 400 + 400 + 404 + (size_t)n_mel * BAND_STRIDE + 2 * n_mel + n_mel / 8 + 8;
     return fl * 4;
 }
 
@@ -326,25 +357,44 @@ int mel_setup_tables(nb200_ctx *ctx) {
 }
 
 int mel_setup_filters(nb200_ctx *ctx, const float *filters, int n_mel) {
-    std::vector<float> vals((size_t)n_mel * MEL_BAND, 0.f);
-    std::vector<int> start(n_mel, 0), len(n_mel, 0);
+    // Banded rows, re-ordered into SLOTS of 8 rows of similar length (one row per lane of a frame's 8-lane group) so the
+    // projection loop has a warp-uniform trip count: entry e = slot*8 + lane holds (mel row, first bin, padded weights).
+    std::vector<int> lo(n_mel, 0), len(n_mel, 0);
     for (int m = 0; m < n_mel; ++m) {
-        int lo = -1, hi = -1;
+        int l = -1, h = -1;
         for (int k = 0; k < N_BINS; ++k)
             if (filters[(size_t)m * N_BINS + k] != 0.0f) {
-                if (lo < 0) lo = k;
-                hi = k;
+                if (l < 0) l = k;
+                h = k;
             }
-        if (lo < 0) continue;
-        if (hi - lo + 1 > MEL_BAND)
-            return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "mel filter row %d spans %d bins (> %d)", m, hi - lo + 1, MEL_BAND);
-        start[m] = lo;
-        len[m] = hi - lo + 1;
-        for (int k = lo; k <= hi; ++k) vals[(size_t)m * MEL_BAND + (k - lo)] = filters[(size_t)m * N_BINS + k];
+        if (l < 0) continue;
+        if (h - l + 1 > MEL_BAND)
+            return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "mel filter row %d spans %d bins (> %d)", m, h - l + 1, MEL_BAND);
+        lo[m] = l;
+        len[m] = h - l + 1;
+    }
+    std::vector<int> order(n_mel);
+    for (int m = 0; m < n_mel; ++m) order[m] = m;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] < len[b]; });
+    std::vector<float> vals((size_t)n_mel * MEL_BAND, 0.f);
+    std::vector<int> start(n_mel, 0), row(n_mel, 0), slen(n_mel / 8, 0);
+    for (int s = 0; s < n_mel / 8; ++s) {
+        int L = 1;
+        for (int l = 0; l < 8; ++l) L = std::max(L, len[order[s * 8 + l]]);
+        slen[s] = L;
+        for (int l = 0; l < 8; ++l) {
+            const int e = s * 8 + l, m = order[e];
+            int st = std::min(lo[m], N_BINS - L);  // keep every read inside the 201 valid power bins
+            if (st < 0) st = 0;
+            row[e] = m;
+            start[e] = st;
+            for (int k = lo[m]; k < lo[m] + len[m]; ++k) vals[(size_t)e * MEL_BAND + (k - st)] = filters[(size_t)m * N_BINS + k];
+        }
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->filt_vals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->filt_start, start.data(), n_mel * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->filt_len, len.data(), n_mel * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->filt_len, row.data(), n_mel * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mel_slot_len, slen.data(), (n_mel / 8) * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return NB200_OK;
 }
@@ -358,9 +408,10 @@ int launch_mel(nb200_ctx *ctx, int n_windows) {
     }
     {
         KernelScope ks(ctx, NB200_K_MEL);
-        dim3 grid(ceil_div(N_FRAMES, FR_PER_CTA), n_windows);
-        mel_kernel<<<grid, MEL_THREADS, smem, ctx->stream>>>(ctx->pcm, ctx->pcm_len, ctx->mel_tables, ctx->filt_vals,
-                                                             ctx->filt_start, ctx->filt_len, n_mel, ctx->logmel, ctx->mel_max);
+        const int tpw = ceil_div(N_FRAMES, FR_PER_CTA), n_tiles = tpw * n_windows;
+        const int grid = n_tiles < 2 * ctx->sm_count ? n_tiles : 2 * ctx->sm_count;  // persistent: 2 CTAs per SM
+        mel_kernel<<<grid, MEL_THREADS, smem, ctx->stream>>>(ctx->pcm, ctx->pcm_len, ctx->mel_tables, ctx->filt_vals, ctx->filt_start,
+                                                             ctx->filt_len, ctx->mel_slot_len, n_mel, n_tiles, tpw, ctx->logmel, ctx->mel_max);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;

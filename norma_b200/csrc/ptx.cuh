@@ -223,6 +223,16 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;
     return d;
 }
+// same descriptor format without swizzle (layout type 0, "interleave"): core matrices of 8 rows x 16 bytes are contiguous
+// 128-byte blocks; for a K-major operand LBO is the stride between K-adjacent core matrices, SBO between 8-row groups
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // instruction descriptor, kind::f16: bf16 A/B, f32 accumulate; a_major/b_major: 0 = K-major, 1 = MN-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_major, int b_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16) |

@@ -25,7 +25,7 @@ SYMBOLS = [
     "nb200_pcm_to_mel", "nb200_pcm_to_mel_batch", "nb200_encoder_forward", "nb200_transcode_batch", "nb200_stage_pcm",
     "nb200_run_resident", "nb200_fetch_features", "nb200_fetch_mel", "nb200_decoder_forward", "nb200_final_linear",
     "nb200_reset_kv_cache", "nb200_decode_greedy", "nb200_timer_start", "nb200_timer_stop", "nb200_profile_enable",
-    "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_gemm_perf", "nb200_test_attention",
+    "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_gemm_perf", "nb200_test_attention", "nb200_test_attention_perf",
     "nb200_decode", "nb200_model_create", "nb200_model_destroy", "nb200_model_last_error", "nb200_model_set_vocab", "nb200_model_transcribe",
     "nb200_model_state", "nb200_model_script_push", "nb200_model_script_log",
 ]
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
         "nb200_test_gemm": ([p, p, p, f32p, i, i, i, i, f32p], i),
         "nb200_test_gemm_perf": ([p, i, i, i, i, i, f32p], i),
         "nb200_test_attention": ([p, f32p, i, i, i, f32p], i),
+        "nb200_test_attention_perf": ([p, f32p, i, i, i, i, f32p], i),
         "nb200_decode": ([p, sz, C.c_float, C.c_uint64, sz, u32p, C.POINTER(sz), C.POINTER(C.c_double), C.POINTER(C.c_double)], i),
         "nb200_model_create": ([p, C.POINTER(SpecialTokens), sz, C.c_uint64, C.POINTER(p)], i),
         "nb200_model_destroy": ([p], None),
@@ -339,6 +340,12 @@ class Context:
     def test_gemm_perf(self, M: int, N: int, K: int, epi_kind: int, iters: int = 20) -> float:
         ms = C.c_float()
         self._ck(self.lib.nb200_test_gemm_perf(self.h, M, N, K, epi_kind, iters, C.byref(ms)))
+        return ms.value
+
+    def test_attention_perf(self, qkv: np.ndarray, B: int, T: int, n_heads: int, iters: int = 20) -> float:
+        qkv = np.ascontiguousarray(qkv, np.float32)
+        ms = C.c_float()
+        self._ck(self.lib.nb200_test_attention_perf(self.h, _f32p(qkv), B, T, n_heads, iters, C.byref(ms)))
         return ms.value
 
     def test_attention(self, qkv: np.ndarray, B: int, T: int, n_heads: int) -> np.ndarray:

@@ -98,10 +98,11 @@ def test_temperature_sampler_distribution_and_determinism(lib):
     counts = collections.Counter()
     n = 300
     for seed in range(n):
-        r = ctx.decode(2, 1.0, seed=seed, max_new_tokens=1)
+        r = ctx.decode(2, 1.0, seed=seed, max_new_tokens=2)  # 2: a lone trailing timestamp would be stripped (model.rs:375-381)
         for b in range(2):
             first = r[b]["tokens"][3]
             assert st.ts_zero <= first <= st.ts_one and r[b]["tokens"][-1] == st.eot
+            assert r[b]["tokens"][4] < st.no_timestamps  # after [task, <|t|>] only text is allowed (model.rs:256-259)
             counts[first] += 1
     expect = 1.0 / (1.0 + 50.0 * np.exp(-1.0))
     freq = counts[plan[2]] / (2 * n)
