@@ -192,6 +192,9 @@ int alloc_decoder(nb200_ctx *ctx) {
     NB_TRY(dev_alloc_t(ctx, B, &ctx->d_nsampled, true));
     NB_TRY(dev_alloc_t(ctx, B, &ctx->d_sumlp, true));
     NB_TRY(dev_alloc_t(ctx, B, &ctx->d_nospeech, true));
+    NB_TRY(dev_alloc(ctx, 64, &ctx->d_dyn, true));
+    NB_TRY(dev_alloc(ctx, B * 32 * (8 + 32), &ctx->d_sel_ws, true));
+    NB_TRY(dev_alloc_t(ctx, B * (size_t)c.decoder_attention_heads * 8 * 66, &ctx->d_attn_ws, true));
     NB_TRY(dev_alloc_t(ctx, (size_t)c.vocab_size, &ctx->suppress, true));
     return NB200_OK;
 }
@@ -410,6 +413,7 @@ void nb200_destroy(nb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->ordinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &g : ctx->step_graphs) cudaGraphExecDestroy(g.second);
     for (void *p : ctx->allocs) cudaFree(p);
     for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -779,20 +783,50 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     // `decoder_forward(prompt, audio_features, flush = true)` (model.rs:297-299): rebuild the cross K/V cache
     NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
     NB_TRY(decoder_init_state(ctx, B));
+    NB_TRY(decoder_set_dyn(ctx, 0, (int)max_new_tokens, temperature, seed, 1));
     for (int pos = 0; pos < plen; ++pos) {
         NB_TRY(decoder_step(ctx, 0, B, pos, pos == 0 || pos == plen - 1));
         if (pos == 0) NB_TRY(decoder_nospeech(ctx, B));
     }
-    NB_TRY(decoder_select(ctx, B, (int)max_new_tokens, temperature, seed));
+    const int greedy = temperature == 0.0f ? 1 : 0;
+    NB_TRY(decoder_select(ctx, B, greedy));  // first sampled token; advances the device position to plen
+    // Steady state: one decode step (embed .. 2 x attention .. MLP .. logits .. select) is a CUDA graph replayed with the
+    // position living on the device; the host only polls the done flags every POLL steps (no per-token sync or transfer).
     std::vector<int> done(B);
-    for (int pos = plen; pos < P; ++pos) {
+    const bool use_graph = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (use_graph) {
+        const int gkey = B * 2 + greedy;
+        auto it = ctx->step_graphs.find(gkey);
+        if (it == ctx->step_graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            int st = decoder_step(ctx, 0, B, -1, 1);
+            if (st == NB200_OK) st = decoder_select(ctx, B, greedy);
+            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+            if (st != NB200_OK) return st;
+            if (ce != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph capture failed: %s", cudaGetErrorString(ce));
+            CUDA_TRY(ctx, cudaGraphInstantiate(&gexec, graph, 0));
+            cudaGraphDestroy(graph);
+            ctx->step_graphs[gkey] = gexec;
+        } else gexec = it->second;
+    }
+    const int POLL = 16;
+    for (int pos = plen; pos < P;) {
         CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         bool all = true;
         for (int b = 0; b < B; ++b) all &= done[b] != 0;
         if (all) break;
-        NB_TRY(decoder_step(ctx, 0, B, pos, 1));
-        NB_TRY(decoder_select(ctx, B, (int)max_new_tokens, temperature, seed));
+        const int n = use_graph ? std::min(POLL, P - pos) : 1;
+        for (int i = 0; i < n; ++i) {
+            if (use_graph) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            else {
+                NB_TRY(decoder_step(ctx, 0, B, -1, 1));
+                NB_TRY(decoder_select(ctx, B, greedy));
+            }
+        }
+        pos += n;
     }
     std::vector<uint32_t> toks((size_t)B * P);
     std::vector<int> len(B);

@@ -128,6 +128,10 @@ struct nb200_ctx {
     int *d_len = nullptr, *d_last_ts = nullptr, *d_done = nullptr, *d_nsampled = nullptr;
     double *d_sumlp = nullptr;
     float *d_nospeech = nullptr;
+    void *d_sel_ws = nullptr;    // greedy select partials: [max_batch][32] float2 + [max_batch][32] SelCand
+    float *d_attn_ws = nullptr;  // split-K decode attention partials [max_batch][heads][8][66]
+    void *d_dyn = nullptr;  // DecodeDyn (decoder.cu): device-resident position / temperature / seed / token budget
+    std::map<int, cudaGraphExec_t> step_graphs;  // captured decode step (embed .. logits .. select) per batch size
     float *suppress = nullptr;  // [V] additive mask (0 / -inf): Config::suppress_tokens U {no_timestamps}
     nb200_special_tokens tok{};
     std::vector<uint32_t> suppress_ids;
@@ -204,7 +208,8 @@ int simt_init(nb200_ctx *ctx);
 int gemm_tc_init(nb200_ctx *ctx);
 int attn_tc_init(nb200_ctx *ctx);
 int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box);
-int decoder_select(nb200_ctx *ctx, int n_windows, int max_new_tokens, float temperature, unsigned long long seed);
+int decoder_select(nb200_ctx *ctx, int n_windows, int greedy);  // also advances the device-resident position
+int decoder_set_dyn(nb200_ctx *ctx, int pos, int max_new, float temperature, unsigned long long seed, int set_params);
 int decoder_nospeech(nb200_ctx *ctx, int n_windows);
 int decoder_init_state(nb200_ctx *ctx, int n_windows);
 // api.cu
