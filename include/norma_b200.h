@@ -173,6 +173,15 @@ NB200_API int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_enco
 NB200_API int nb200_model_script_push(nb200_model *m, double avg_logprob, double no_speech_prob, const uint32_t *tokens, size_t n);
 NB200_API int nb200_model_script_log(nb200_model *m, size_t i, size_t *encode_len, double *decode_temp);
 
+/* ---- streaming front half (BASELINE config 4): what `Packer` + the re-mel of the whole buffer on every chunk
+ *      (src/lib.rs:224-262, model.rs:68-74) become on the device.  Window 0 only.  push appends PCM and recomputes only the mel
+ *      frames the new samples touch; drain drops samples from the front (norma's seek, model.rs:110,126-127); features
+ *      normalises with the global max over the buffered audio (exactly pcm_to_mel of those samples) and runs the encoder. --- */
+NB200_API int nb200_stream_reset(nb200_ctx *ctx);
+NB200_API int nb200_stream_push(nb200_ctx *ctx, const float *chunk, size_t n);
+NB200_API int nb200_stream_drain(nb200_ctx *ctx, size_t n);
+NB200_API int nb200_stream_features(nb200_ctx *ctx, int run_encoder, float *mel_out /* [n_mel][3000] or NULL */, float *features_out /* or NULL */);
+
 /* ---- measurement helpers (bench.py): CUDA events on the ctx stream ------------------------------------ */
 NB200_API int nb200_timer_start(nb200_ctx *ctx);
 NB200_API int nb200_timer_stop(nb200_ctx *ctx, float *ms);          /* records, synchronises, returns elapsed ms */

@@ -862,6 +862,65 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     return NB200_OK;
 }
 
+// ---- streaming front half (BASELINE config 4): the window-0 PCM lives on the device, small chunks are
+// appended as they arrive and only the mel frames they touch are recomputed -------------------------------------------
+int nb200_stream_reset(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, true));
+    ctx->stream_len = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->pcm, 0, (size_t)N_SAMPLES * 4, ctx->stream));
+    return mel_stream_reset(ctx);
+}
+
+int nb200_stream_push(nb200_ctx *ctx, const float *chunk, size_t n) {
+    NB_TRY(check_ready(ctx, false, true));
+    if ((n && !chunk) || ctx->stream_len + n > (size_t)N_SAMPLES)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "stream_push: %zu samples do not fit the 30 s window (%d buffered)", n, ctx->stream_len);
+    if (n == 0) return NB200_OK;
+    const int n_old = ctx->stream_len, n_new = n_old + (int)n;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm + n_old, chunk, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm_len, &n_new, 4, cudaMemcpyHostToDevice, ctx->stream));
+    // frame i = samples [160 i, 160 i + 400): frames that were still zero-filled at n_old change, frames starting before n_new appear
+    const int f_lo = n_old >= N_FFT ? (n_old - N_FFT) / HOP + 1 : 0;
+    const int f_hi = std::min(N_FRAMES, (n_new + HOP - 1) / HOP);
+    NB_TRY(mel_stream_update(ctx, f_lo, f_hi));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `chunk` and `n_new` are consumed
+    ctx->stream_len = n_new;
+    return NB200_OK;
+}
+
+int nb200_stream_drain(nb200_ctx *ctx, size_t n) {
+    NB_TRY(check_ready(ctx, false, true));
+    if (n > (size_t)ctx->stream_len) return nb200_fail(ctx, NB200_INVALID_ARG, "stream_drain: %zu > %d buffered samples", n, ctx->stream_len);
+    if (n == 0) return NB200_OK;
+    const int n_new = ctx->stream_len - (int)n;
+    if (!ctx->stream_tmp) NB_TRY(dev_alloc_t(ctx, (size_t)N_SAMPLES + (size_t)ctx->cfg.num_mel_bins * N_FRAMES, &ctx->stream_tmp));
+    NB_TRY(mel_stream_shift(ctx, (int)n, n_new, ctx->stream_tmp, ctx->stream_tmp + N_SAMPLES));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm_len, &n_new, 4, cudaMemcpyHostToDevice, ctx->stream));
+    // frames keep their values when the shift is a whole number of hops; otherwise (and for the frames that now reach past
+    // the end) recompute
+    const int f_lo = (n % HOP == 0) ? (n_new >= N_FFT ? (n_new - N_FFT) / HOP + 1 : 0) : 0;
+    NB_TRY(mel_stream_update(ctx, f_lo, N_FRAMES));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream_len = n_new;
+    return NB200_OK;
+}
+
+// log-mel of the buffered audio exactly as pcm_to_mel would return it for those samples (first 3000 frames), then the encoder
+int nb200_stream_features(nb200_ctx *ctx, int run_encoder, float *mel_out, float *features_out) {
+    NB_TRY(check_ready(ctx, run_encoder != 0, true));
+    NB_TRY(mel_stream_window_max(ctx));
+    NB_TRY(launch_mel_norm(ctx, 1));
+    if (mel_out) CUDA_TRY(ctx, cudaMemcpyAsync(mel_out, ctx->mel_norm, (size_t)ctx->cfg.num_mel_bins * N_FRAMES * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (run_encoder) {
+        NB_TRY(encoder_run(ctx, 1));
+        if (features_out)
+            CUDA_TRY(ctx, cudaMemcpyAsync(features_out, ctx->enc_out, (size_t)ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
 int nb200_timer_start(nb200_ctx *ctx) {
     NB_TRY(check_ready(ctx, false, false));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));

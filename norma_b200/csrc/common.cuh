@@ -105,6 +105,8 @@ struct nb200_ctx {
     float *mel_norm = nullptr;    // [max_batch][n_mel][N_FRAMES] normalised f32 (reference layout)
     void *melT = nullptr;         // [max_batch][N_FRAMES+2][n_mel] time-major, zero pad rows 0 and N_FRAMES+1
     size_t *host_lens = nullptr;
+    int stream_len = 0;           // streaming (window 0): samples currently buffered on the device
+    float *stream_tmp = nullptr;  // scratch for the seek shift: [N_SAMPLES] + [n_mel][N_FRAMES]
 
     // encoder activations
     void *y1 = nullptr;     // [max_batch][N_FRAMES+1][d] conv1 out, row 0 = zero pad (compute dtype)
@@ -188,6 +190,10 @@ int launch_mel(nb200_ctx *ctx, int n_windows);            // pcm -> logmel (+ ru
 int launch_mel_norm(nb200_ctx *ctx, int n_windows);       // logmel -> mel_norm (f32, reference layout) + melT
 int launch_mel_from_host_layout(nb200_ctx *ctx, int n_windows);  // mel_norm (already normalised) -> melT
 int mel_setup_tables(nb200_ctx *ctx);
+int mel_stream_reset(nb200_ctx *ctx);
+int mel_stream_update(nb200_ctx *ctx, int f_lo, int f_hi);
+int mel_stream_window_max(nb200_ctx *ctx);
+int mel_stream_shift(nb200_ctx *ctx, int ns, int new_len, float *tmp_pcm, float *tmp_lm);
 int mel_setup_filters(nb200_ctx *ctx, const float *filters, int n_mel);
 // simt.cu
 int launch_gemm_f32(nb200_ctx *ctx, const float *A, const float *W, const GemmShape &s, const Epilogue &e);

@@ -83,7 +83,7 @@ __global__ void mel_init_max_kernel(unsigned *mel_max, int n) {
 __global__ void __launch_bounds__(MEL_THREADS, 2)
 mel_kernel(const float *__restrict__ pcm, const int *__restrict__ pcm_len, const float *__restrict__ tables,
            const float *__restrict__ filt_vals, const int *__restrict__ filt_start, const int *__restrict__ filt_row,
-           const int *__restrict__ slot_len, int n_mel, int n_tiles, int tiles_per_window, float *__restrict__ logmel,
+           const int *__restrict__ slot_len, int n_mel, int n_tiles, int tiles_per_window, int tile0, float *__restrict__ logmel,
            unsigned *__restrict__ mel_max) {
     extern __shared__ __align__(16) float smem[];
     float *s_pcm = smem;                                  // PCM_SMEM (aliased by s_out after the FFT loads)
@@ -139,7 +139,7 @@ mel_kernel(const float *__restrict__ pcm, const int *__restrict__ pcm_len, const
             pf[u] = v;
         }
     };
-    int tile = blockIdx.x;
+    int tile = tile0 + blockIdx.x;
     if (tile < n_tiles) prefetch(tile);
 
     const int n2 = lane & 7, grp = lane >> 3;
@@ -411,7 +411,7 @@ int launch_mel(nb200_ctx *ctx, int n_windows) {
         const int tpw = ceil_div(N_FRAMES, FR_PER_CTA), n_tiles = tpw * n_windows;
         const int grid = n_tiles < 2 * ctx->sm_count ? n_tiles : 2 * ctx->sm_count;  // persistent: 2 CTAs per SM
         mel_kernel<<<grid, MEL_THREADS, smem, ctx->stream>>>(ctx->pcm, ctx->pcm_len, ctx->mel_tables, ctx->filt_vals, ctx->filt_start,
-                                                             ctx->filt_len, ctx->mel_slot_len, n_mel, n_tiles, tpw, ctx->logmel, ctx->mel_max);
+                                                             ctx->filt_len, ctx->mel_slot_len, n_mel, n_tiles, tpw, 0, ctx->logmel, ctx->mel_max);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;
@@ -425,6 +425,81 @@ static int launch_norm_impl(nb200_ctx *ctx, int n_windows, const float *in, int 
         mel_norm_kernel<bf16><<<grid, block, 0, ctx->stream>>>(in, ctx->mel_max, raw, n_mel, mel_norm, (bf16 *)ctx->melT);
     else
         mel_norm_kernel<float><<<grid, block, 0, ctx->stream>>>(in, ctx->mel_max, raw, n_mel, mel_norm, (float *)ctx->melT);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+namespace {
+// streaming helpers (window 0): running max over the frames that hold data, frame shift when norma seeks forward
+__global__ void mel_window_max_kernel(const float *__restrict__ logmel, int n_mel, unsigned *__restrict__ mel_max) {
+    __shared__ float red[32];
+    float m = -10.0f;  // candle's zero-pad frames
+    for (int i = threadIdx.x; i < n_mel * N_FRAMES; i += blockDim.x) m = fmaxf(m, logmel[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+        mel_max[0] = enc_max(m);
+    }
+}
+__global__ void fill_kernel(float *p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// out-of-place shift of window 0: pcm by `ns` samples, logmel by `nf` frames (tail filled with silence)
+__global__ void stream_shift_kernel(const float *__restrict__ pcm_in, float *__restrict__ pcm_out, int ns, int new_len, const float *__restrict__ lm_in,
+                                    float *__restrict__ lm_out, int nf, int n_mel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N_SAMPLES) pcm_out[i] = (i < new_len) ? pcm_in[i + ns] : 0.f;
+    if (i < n_mel * N_FRAMES) {
+        const int m = i / N_FRAMES, f = i - m * N_FRAMES;
+        lm_out[i] = (f + nf < N_FRAMES) ? lm_in[m * N_FRAMES + f + nf] : -10.0f;
+    }
+}
+}  // namespace
+
+int mel_stream_reset(nb200_ctx *ctx) {
+    KernelScope ks(ctx, NB200_K_MISC);
+    const size_t n = (size_t)ctx->cfg.num_mel_bins * N_FRAMES;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->logmel, -10.0f, n);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->pcm_len, 0, 4, ctx->stream));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+// recompute the 32-frame tiles of window 0 that contain frames [f_lo, f_hi)
+int mel_stream_update(nb200_ctx *ctx, int f_lo, int f_hi) {
+    const int n_mel = ctx->cfg.num_mel_bins;
+    const int tpw = ceil_div(N_FRAMES, FR_PER_CTA);
+    int t0 = f_lo / FR_PER_CTA, t1 = ceil_div(f_hi, FR_PER_CTA);
+    if (t1 > tpw) t1 = tpw;
+    if (t0 >= t1) return NB200_OK;
+    KernelScope ks(ctx, NB200_K_MEL);
+    mel_kernel<<<t1 - t0, MEL_THREADS, mel_smem_bytes(n_mel), ctx->stream>>>(ctx->pcm, ctx->pcm_len, ctx->mel_tables, ctx->filt_vals, ctx->filt_start,
+                                                                            ctx->filt_len, ctx->mel_slot_len, n_mel, t1, tpw, t0, ctx->logmel, ctx->mel_max);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+int mel_stream_window_max(nb200_ctx *ctx) {
+    KernelScope ks(ctx, NB200_K_MEL_NORM);
+    mel_window_max_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->logmel, ctx->cfg.num_mel_bins, ctx->mel_max);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+// drop `ns` samples (and ns / 160 frames) from the front of window 0; scratch = mel_norm (pcm) and logmel row of window 1.. is
+// not available for max_batch = 1, so the shift goes through a temporary allocation owned by the ctx
+int mel_stream_shift(nb200_ctx *ctx, int ns, int new_len, float *tmp_pcm, float *tmp_lm) {
+    const int n_mel = ctx->cfg.num_mel_bins;
+    const int nf = ns / HOP;
+    KernelScope ks(ctx, NB200_K_MISC);
+    const int n = N_SAMPLES > n_mel * N_FRAMES ? N_SAMPLES : n_mel * N_FRAMES;
+    stream_shift_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(ctx->pcm, tmp_pcm, ns, new_len, ctx->logmel, tmp_lm, nf, n_mel);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pcm, tmp_pcm, (size_t)N_SAMPLES * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->logmel, tmp_lm, (size_t)n_mel * N_FRAMES * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;
 }

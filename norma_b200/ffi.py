@@ -28,6 +28,7 @@ SYMBOLS = [
     "nb200_profile_read", "nb200_profile_reset", "nb200_flush_l2", "nb200_test_gemm", "nb200_test_gemm_perf", "nb200_test_attention", "nb200_test_attention_perf",
     "nb200_decode", "nb200_model_create", "nb200_model_destroy", "nb200_model_last_error", "nb200_model_set_vocab", "nb200_model_transcribe",
     "nb200_model_state", "nb200_model_script_push", "nb200_model_script_log",
+    "nb200_stream_reset", "nb200_stream_push", "nb200_stream_drain", "nb200_stream_features",
 ]
 
 
@@ -102,6 +103,10 @@ def load_library() -> C.CDLL:
         "nb200_model_state": ([p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)], i),
         "nb200_model_script_push": ([p, C.c_double, C.c_double, u32p, sz], i),
         "nb200_model_script_log": ([p, sz, C.POINTER(sz), C.POINTER(C.c_double)], i),
+        "nb200_stream_reset": ([p], i),
+        "nb200_stream_push": ([p, f32p, sz], i),
+        "nb200_stream_drain": ([p, sz], i),
+        "nb200_stream_features": ([p, i, f32p, f32p], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
@@ -265,6 +270,24 @@ class Context:
         out = np.empty((self.n_mel, 3000), np.float32)
         self._ck(self.lib.nb200_fetch_mel(self.h, window, _f32p(out), out.size))
         return out
+
+    # -- streaming (window 0) ----------------------------------------------------------------------------------
+    def stream_reset(self):
+        self._ck(self.lib.nb200_stream_reset(self.h))
+
+    def stream_push(self, chunk: np.ndarray):
+        chunk = np.ascontiguousarray(chunk, np.float32)
+        if chunk.size:
+            self._ck(self.lib.nb200_stream_push(self.h, _f32p(chunk), chunk.size))
+
+    def stream_drain(self, n: int):
+        self._ck(self.lib.nb200_stream_drain(self.h, n))
+
+    def stream_features(self, run_encoder=True, want_mel=False, want_features=False):
+        mel = np.empty((self.n_mel, 3000), np.float32) if want_mel else None
+        feat = np.empty((self.T, self.d), np.float32) if want_features else None
+        self._ck(self.lib.nb200_stream_features(self.h, int(run_encoder), _f32p(mel), _f32p(feat)))
+        return mel, feat
 
     # -- seams (3)-(5) ---------------------------------------------------------------------------------------
     def decoder_forward(self, tokens: Sequence[int], flush: bool, window: int = 0) -> np.ndarray:
