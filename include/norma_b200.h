@@ -124,6 +124,11 @@ NB200_API int nb200_encoder_forward(nb200_ctx *ctx, const float *mel, size_t n_w
 /* ---- fused front half for throughput configs (BASELINE configs 2, 3, 5): PCM -> log-mel -> encoder in one
  *      call; H2D of PCM, both stages and (if out != NULL) the D2H of the features happen inside. ---------- */
 NB200_API int nb200_transcode_batch(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *out);
+/* pipelined form: submit enqueues H2D (own stream) -> log-mel + encoder -> D2H (own stream) for one batch and returns; at most two
+ * batches may be in flight; collect blocks until the OLDEST submitted batch's features are in its `out`.  `pcm` and `out` must stay
+ * valid (and should be pinned) until that batch is collected.  Batch k+1's upload and batch k-1's download overlap batch k's compute. */
+NB200_API int nb200_transcode_submit(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *out);
+NB200_API int nb200_transcode_collect(nb200_ctx *ctx);
 /* the same on inputs already resident in HBM (bench `value`): stage once, run many times */
 NB200_API int nb200_stage_pcm(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens);
 NB200_API int nb200_run_resident(nb200_ctx *ctx, size_t n_windows, int do_mel, int do_encoder);

@@ -420,6 +420,14 @@ void nb200_destroy(nb200_ctx *ctx) {
     if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
     if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_mel[i]) cudaEventDestroy(ctx->ev_mel[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -667,6 +675,89 @@ int nb200_transcode_batch(nb200_ctx *ctx, const float *pcm, size_t n_windows, si
         CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out, n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
                                       ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+// ---- pipelined batches: batch k+1's PCM goes up and batch k-1's features come down while batch k computes --------------
+static int pipe_init(nb200_ctx *ctx) {
+    if (ctx->h2d_stream) return NB200_OK;
+    const size_t B = ctx->cfg.max_batch, per_out = (size_t)ctx->cfg.max_source_positions * ctx->cfg.d_model;
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    ctx->pipe_pcm[0] = ctx->pcm;  // slot 0 reuses the synchronous path's buffers
+    ctx->pipe_len[0] = ctx->pcm_len;
+    ctx->pipe_out[0] = ctx->enc_out;
+    NB_TRY(dev_alloc_t(ctx, B * N_SAMPLES, &ctx->pipe_pcm[1], true));
+    NB_TRY(dev_alloc_t(ctx, B, &ctx->pipe_len[1], true));
+    NB_TRY(dev_alloc_t(ctx, B * per_out, &ctx->pipe_out[1]));
+    for (int s = 0; s < 2; ++s) {
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_h2d[s], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_mel[s], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[s], cudaEventDisableTiming));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_d2h[s], cudaEventDisableTiming));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_transcode_submit(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *out) {
+    NB_TRY(check_ready(ctx, true, true));
+    if (!pcm || !out || n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "transcode_submit: n_windows=%zu (max_batch %d)", n_windows, ctx->cfg.max_batch);
+    if (ctx->pipe_submitted - ctx->pipe_collected >= 2)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "transcode_submit: two batches are already in flight; call nb200_transcode_collect first");
+    NB_TRY(pipe_init(ctx));
+    const int s = (int)(ctx->pipe_submitted & 1);
+    std::vector<int> &l = ctx->pipe_lens_host[s];
+    l.resize(n_windows);
+    for (size_t w = 0; w < n_windows; ++w) {
+        const size_t n = lens ? lens[w] : stride;
+        if (n > (size_t)N_SAMPLES) return nb200_fail(ctx, NB200_INVALID_ARG, "window %zu has %zu samples (> %d)", w, n, N_SAMPLES);
+        l[w] = (int)n;
+    }
+    // H2D on its own stream, after the mel kernel that last read this slot's PCM (two submits ago)
+    if (ctx->pipe_submitted >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->h2d_stream, ctx->ev_mel[s], 0));
+    for (size_t w = 0; w < n_windows; ++w)
+        if (l[w]) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pipe_pcm[s] + w * N_SAMPLES, pcm + w * stride, (size_t)l[w] * 4, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pipe_len[s], l.data(), n_windows * 4, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_h2d[s], ctx->h2d_stream));
+    // compute: needs the PCM, and the feature buffer of this slot must have been drained by the D2H of two submits ago
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[s], 0));
+    if (ctx->pipe_submitted >= 2) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[s], 0));
+    float *save_pcm = ctx->pcm, *save_out = ctx->enc_out;
+    int *save_len = ctx->pcm_len;
+    ctx->pcm = ctx->pipe_pcm[s];
+    ctx->pcm_len = ctx->pipe_len[s];
+    ctx->enc_out = ctx->pipe_out[s];
+    if (ctx->compute == NB200_F32) ctx->enc_out_c = ctx->enc_out;
+    int st = launch_mel(ctx, (int)n_windows);
+    if (st == NB200_OK) {
+        cudaEventRecord(ctx->ev_mel[s], ctx->stream);
+        st = launch_mel_norm(ctx, (int)n_windows);
+    }
+    if (st == NB200_OK) st = encoder_run(ctx, (int)n_windows);
+    ctx->pcm = save_pcm;
+    ctx->pcm_len = save_len;
+    ctx->enc_out = save_out;
+    if (ctx->compute == NB200_F32) ctx->enc_out_c = ctx->enc_out;
+    if (s != 0) ctx->n_resident = 0;  // the resident-features slot (decoder input) is slot 0 only
+    if (st != NB200_OK) return st;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_comp[s], ctx->stream));
+    // D2H on its own stream
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_comp[s], 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->pipe_out[s], n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
+                                  ctx->d2h_stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_d2h[s], ctx->d2h_stream));
+    ctx->pipe_submitted++;
+    return NB200_OK;
+}
+
+int nb200_transcode_collect(nb200_ctx *ctx) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (ctx->pipe_collected >= ctx->pipe_submitted) return nb200_fail(ctx, NB200_INVALID_ARG, "transcode_collect: nothing in flight");
+    const int s = (int)(ctx->pipe_collected & 1);
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_d2h[s]));
+    ctx->pipe_collected++;
     return NB200_OK;
 }
 

@@ -105,6 +105,14 @@ struct nb200_ctx {
     float *mel_norm = nullptr;    // [max_batch][n_mel][N_FRAMES] normalised f32 (reference layout)
     void *melT = nullptr;         // [max_batch][N_FRAMES+2][n_mel] time-major, zero pad rows 0 and N_FRAMES+1
     size_t *host_lens = nullptr;
+    // pipelined batches (nb200_transcode_submit / _collect): two slots of PCM and feature buffers, copies on their own streams
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    float *pipe_pcm[2] = {nullptr, nullptr};
+    int *pipe_len[2] = {nullptr, nullptr};
+    float *pipe_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_mel[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    std::vector<int> pipe_lens_host[2];
+    long long pipe_submitted = 0, pipe_collected = 0;
     int stream_len = 0;           // streaming (window 0): samples currently buffered on the device
     float *stream_tmp = nullptr;  // scratch for the seek shift: [N_SAMPLES] + [n_mel][N_FRAMES]
 

@@ -29,6 +29,7 @@ SYMBOLS = [
     "nb200_decode", "nb200_model_create", "nb200_model_destroy", "nb200_model_last_error", "nb200_model_set_vocab", "nb200_model_transcribe",
     "nb200_model_state", "nb200_model_script_push", "nb200_model_script_log",
     "nb200_stream_reset", "nb200_stream_push", "nb200_stream_drain", "nb200_stream_features",
+    "nb200_transcode_submit", "nb200_transcode_collect",
 ]
 
 
@@ -103,6 +104,8 @@ def load_library() -> C.CDLL:
         "nb200_model_state": ([p, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)], i),
         "nb200_model_script_push": ([p, C.c_double, C.c_double, u32p, sz], i),
         "nb200_model_script_log": ([p, sz, C.POINTER(sz), C.POINTER(C.c_double)], i),
+        "nb200_transcode_submit": ([p, f32p, sz, sz, C.POINTER(sz), f32p], i),
+        "nb200_transcode_collect": ([p], i),
         "nb200_stream_reset": ([p], i),
         "nb200_stream_push": ([p, f32p, sz], i),
         "nb200_stream_drain": ([p, sz], i),
@@ -248,6 +251,18 @@ class Context:
             lp = (C.c_size_t * nw)(*[int(x) for x in lens])
         self._ck(self.lib.nb200_transcode_batch(self.h, _f32p(pcm), nw, stride, lp, _f32p(out)))
         return out
+
+    def transcode_submit(self, pcm: np.ndarray, out: np.ndarray, lens=None):
+        """Pipelined form: `pcm` / `out` must be C-contiguous f32 (ideally pinned) and stay alive until collected."""
+        assert pcm.dtype == np.float32 and pcm.flags.c_contiguous and out.dtype == np.float32 and out.flags.c_contiguous
+        nw, stride = pcm.shape
+        lp = None
+        if lens is not None:
+            lp = (C.c_size_t * nw)(*[int(x) for x in lens])
+        self._ck(self.lib.nb200_transcode_submit(self.h, _f32p(pcm), nw, stride, lp, _f32p(out)))
+
+    def transcode_collect(self):
+        self._ck(self.lib.nb200_transcode_collect(self.h))
 
     def stage_pcm(self, pcm: np.ndarray, lens=None):
         pcm = np.ascontiguousarray(pcm, np.float32)

@@ -261,3 +261,23 @@ def test_errors_are_reported_not_fatal(lib):
     with pytest.raises(ffi.Nb200Error):
         ctx.pcm_to_mel_batch(np.zeros((2, 1000), np.float32))    # > max_batch
     ctx.close()
+
+
+def test_pipelined_submit_collect_equals_blocking(lib, tiny):
+    ctx = make_ctx(tiny, "bf16", max_batch=3)
+    pcm = np.ascontiguousarray(tiny["pcm"])
+    ref = ctx.transcode_batch(pcm)
+    outs = [np.empty_like(ref) for _ in range(3)]
+    ctx.transcode_submit(pcm, outs[0])
+    ctx.transcode_submit(pcm[::-1].copy(), outs[1])
+    with pytest.raises(ffi.Nb200Error):
+        ctx.transcode_submit(pcm, outs[2])  # at most two batches in flight
+    ctx.transcode_collect()
+    ctx.transcode_submit(pcm, outs[2])
+    ctx.transcode_collect()
+    ctx.transcode_collect()
+    with pytest.raises(ffi.Nb200Error):
+        ctx.transcode_collect()  # nothing in flight
+    assert np.array_equal(outs[0], ref) and np.array_equal(outs[2], ref)
+    assert np.array_equal(outs[1], ref[::-1])  # windows are independent
+    ctx.close()
