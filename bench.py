@@ -124,6 +124,15 @@ def cpu_port_window(c, weights, n_windows=1, seed0=0):
     return step
 
 
+def workload_config(args, c, world, B):
+    """The `config` object both arms print (the reference arm adds `sample`)."""
+    return {"workload": f"{args.model}-shaped log-mel + encoder ({c['num_mel_bins']} mel, {c['encoder_layers']} x d{c['d_model']}), "
+                        + (f"{args.total_windows} x 30 s windows per step sharded over {world} GPU(s)" if args.total_windows
+                           else f"{B} x 30 s windows per step per GPU") + ", random-init weights",
+            "windows_per_step_per_gpu": B, "parallelism": f"window-sharded x{world}, no collective",
+            "l2": "working set per step (1.27 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"}
+
+
 def run_reference(args, rank):
     """`--impl reference`: the CPU port of the reference path, all host threads, one window per step."""
     if rank != 0:
@@ -143,8 +152,8 @@ def run_reference(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model}-shaped log-mel + encoder, 1 window of 30 s per step, CPU port of the candle path (Rust reference unbuildable here)",
-                   "windows_per_step": 1},
+        "config": dict(workload_config(args, c, max(1, args.gpus), args.windows),
+                       sample="each step = 1 of the workload's 30 s windows through the CPU port of the candle path (Rust reference unbuildable here)"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": "1 x 30 s window per step: C restatement of pcm_to_mel + torch-CPU fp32 encoder"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -306,11 +315,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if args.total_windows else "weak", "vs_baseline": None, "dtype": args.compute, "data": "synthetic",
-            "config": {"workload": f"{args.model}-shaped log-mel + encoder ({c['num_mel_bins']} mel, {c['encoder_layers']} x d{c['d_model']}), "
-                                   + (f"{args.total_windows} x 30 s windows per step sharded over {world} GPU(s)" if args.total_windows
-                                      else f"{B} x 30 s windows per step per GPU") + ", random-init weights",
-                       "windows_per_step_per_gpu": B, "parallelism": f"window-sharded x{world}, no collective",
-                       "l2": "working set per step (1.27 GB bf16 weights + activations) exceeds the 126 MB L2; no explicit flush"},
+            "config": workload_config(args, c, world, B),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "feature_checksum": checksum,
         }
