@@ -41,7 +41,10 @@ typedef enum {
     NB200_OOM = 3,
     NB200_NOT_LOADED = 4,
     NB200_UNSUPPORTED_SHAPE = 5,
-    NB200_ARCH_MISMATCH = 6
+    NB200_ARCH_MISMATCH = 6,
+    NB200_IO_ERROR = 7,     /* whisper::Error::Io: a checkpoint file cannot be read */
+    NB200_PARSE_ERROR = 8,  /* whisper::Error::{Json, LoadTokenizer} / candle's safetensors errors */
+    NB200_NOT_FOUND = 9     /* whisper::Error::TokenId: the tokenizer has no such token (src/models/whisper/mod.rs:86-90) */
 } nb200_status;
 
 /* replaces candle_core::DType as returned by norma's `DType::to_dtype` (src/dtype.rs:15,23) */
@@ -162,6 +165,12 @@ NB200_API int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_n
 NB200_API int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens, uint32_t *tokens_out,
                            size_t *n_tokens, double *avg_logprob, double *no_speech_prob);
 
+/* ---- replaces `Model::detect_language(audio_features)` (model.rs:194-210), multilingual checkpoints only: one decoder pass over
+ *      [sot] with flush = true, the logits of the `n_langs` language tokens (norma: the 99 `Language` variants in declaration
+ *      order, multilingual.rs:251-254), softmax over those alone, and the most probable one (the earlier token on a tie, as the
+ *      reference's stable descending sort).  probs_out (nullable): [n_langs] f32.  n_langs <= 1024. ---------------------- */
+NB200_API int nb200_detect_language(nb200_ctx *ctx, size_t window, const uint32_t *lang_tokens, size_t n_langs, uint32_t *token_out, float *probs_out);
+
 /* ---- host side of norma's whisper `Model` (C++ mirror of model.rs:55-191): buffering, 30 s slicing,
  *      temperature fallback, timestamp segmentation and seek.  ctx = NULL creates a model over a SCRIPTED backend whose
  *      decoding results are pushed with nb200_model_script_push (host-logic tests without a GPU). ------------------- */
@@ -177,6 +186,45 @@ NB200_API int nb200_model_transcribe(nb200_model *m, const float *data, size_t n
 NB200_API int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_encodes, size_t *n_decodes, size_t *n_resets);
 NB200_API int nb200_model_script_push(nb200_model *m, double avg_logprob, double no_speech_prob, const uint32_t *tokens, size_t n);
 NB200_API int nb200_model_script_log(nb200_model *m, size_t i, size_t *encode_len, double *decode_temp);
+
+/* `LanguageState::Detect` (model.rs:392-440; multilingual.rs:319-322): the language is detected with nb200_detect_language on the
+ * first window of every transcription and forgotten on final_chunk (model.rs:154,170-173).  Without this call the model is
+ * `LanguageState::ConstLang(tok.lang)` (monolingual.rs:449).  nb200_model_language: current language token (UINT32_MAX = none yet). */
+NB200_API int nb200_model_set_language_detection(nb200_model *m, const uint32_t *lang_tokens, size_t n);
+NB200_API int nb200_model_language(nb200_model *m, uint32_t *token, size_t *n_detects);
+NB200_API int nb200_model_script_push_language(nb200_model *m, uint32_t token);
+
+/* ---- checkpoint files: what `Definition::blocking_try_to_model` does once hf-hub has fetched config.json,
+ *      tokenizer.json and model.safetensors (monolingual.rs:347-430, multilingual.rs:225-300).  The download is out of scope.
+ *      These are host-only; ctx-less failures leave their message in nb200_last_error(NULL). ----------------------------- */
+typedef enum { NB200_TASK_TRANSCRIBE = 0, NB200_TASK_TRANSLATE = 1 } nb200_task; /* multilingual::Task (multilingual.rs:19-25) */
+/* replaces `serde_json::from_str::<Config>` (monolingual.rs:347).  max_batch is set to 1.  suppress_out (nullable) receives up to
+ * suppress_cap ids of Config::suppress_tokens, *n_suppress their count. */
+NB200_API int nb200_config_from_file(const char *path, nb200_config *cfg, uint32_t *suppress_out, size_t suppress_cap, size_t *n_suppress);
+/* replaces `include_bytes!("./whisper_mel_bytes/{80,128}.bytes")` (monolingual.rs:351-362): out = [n_mel][201] f32 */
+NB200_API int nb200_mel_filters(int n_mel, float *out);
+/* replaces `tokenizers::Tokenizer::from_file` / `token_to_id` / `decode(ids, skip_special_tokens)` (monolingual.rs:348; mod.rs:86-90;
+ * model.rs:147): byte-level BPE vocabulary + added tokens; decode output is NUL-terminated UTF-8, truncated to cap, *len = full length */
+typedef struct nb200_tokenizer nb200_tokenizer;
+NB200_API int nb200_tokenizer_from_file(const char *path, nb200_tokenizer **out);
+NB200_API void nb200_tokenizer_destroy(nb200_tokenizer *t);
+NB200_API int nb200_tokenizer_token_to_id(const nb200_tokenizer *t, const char *token, uint32_t *id);
+NB200_API int nb200_tokenizer_decode(const nb200_tokenizer *t, const uint32_t *ids, size_t n, int skip_special_tokens, char *out, size_t cap, size_t *len);
+/* the id lookups of monolingual.rs:376-384,419-420 / multilingual.rs:239-249; language_token e.g. "<|en|>" or NULL (no language token) */
+NB200_API int nb200_tokenizer_special_tokens(const nb200_tokenizer *t, const char *language_token, int task, nb200_special_tokens *out);
+/* ids of the 99 `Language` tokens in declaration order (languages.rs:7-107; multilingual.rs:251-254): out[99] */
+NB200_API int nb200_tokenizer_language_tokens(const nb200_tokenizer *t, uint32_t *out);
+/* replaces `VarBuilder::from_mmaped_safetensors(&[weights_file], m::DTYPE, &device)` (monolingual.rs:371-372): mmaps the file and
+ * hands every `model.*` tensor (F32 / F16 / BF16 / F64, converted to f32 like candle) to nb200_load_tensor; finalize separately */
+NB200_API int nb200_load_safetensors(nb200_ctx *ctx, const char *path, size_t *n_tensors);
+/* ctx-less read of one tensor converted to f32 (tests, tools): out (nullable) receives min(cap, numel) values, shape up to 8 dims */
+NB200_API int nb200_safetensors_read(const char *path, const char *name, float *out, size_t cap, int64_t *shape, int *rank);
+/* `transcribe` then detokenizes with the tokenizer (a copy is kept) instead of the nb200_model_set_vocab table */
+NB200_API int nb200_model_set_tokenizer(nb200_model *m, const nb200_tokenizer *t);
+/* all of the above in `blocking_try_to_model` order: language_token = "<|en|>".. -> monolingual / MultiAsMono (ConstLang);
+ * NULL -> multilingual (Detect).  On success the caller owns *ctx_out and *model_out (destroy the model first). */
+NB200_API int nb200_model_from_files(int ordinal, const char *config_json, const char *tokenizer_json, const char *safetensors, nb200_dtype compute,
+                                     const char *language_token, int task, size_t max_chunk_len, uint64_t seed, nb200_ctx **ctx_out, nb200_model **model_out);
 
 /* ---- streaming front half (BASELINE config 4): what `Packer` + the re-mel of the whole buffer on every chunk
  *      (src/lib.rs:224-262, model.rs:68-74) become on the device.  Window 0 only.  push appends PCM and recomputes only the mel

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libnorma_b200.so")
-SOURCES = ["api.cu", "mel.cu", "simt.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "decoder.cu", "host/whisper_host.cc"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join("host", "whisper_host.h"), os.path.join("..", "..", "include", "norma_b200.h")]
+SOURCES = ["api.cu", "mel.cu", "simt.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "decoder.cu", "host/whisper_host.cc", "host/loader.cc"]
+HEADERS = ["common.cuh", "ptx.cuh", os.path.join("host", "whisper_host.h"), os.path.join("host", "loader.h"), os.path.join("host", "json.h"), os.path.join("..", "..", "include", "norma_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

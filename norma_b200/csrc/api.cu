@@ -194,6 +194,7 @@ int alloc_decoder(nb200_ctx *ctx) {
     NB_TRY(dev_alloc_t(ctx, B, &ctx->d_nospeech, true));
     NB_TRY(dev_alloc(ctx, 64, &ctx->d_dyn, true));
     NB_TRY(dev_alloc(ctx, B * 32 * (8 + 32), &ctx->d_sel_ws, true));
+    NB_TRY(dev_alloc(ctx, (size_t)NB200_MAX_LANGS * 8 + 16, &ctx->d_lang, true));
     NB_TRY(dev_alloc_t(ctx, B * (size_t)c.decoder_attention_heads * 8 * 66, &ctx->d_attn_ws, true));
     NB_TRY(dev_alloc_t(ctx, (size_t)c.vocab_size, &ctx->suppress, true));
     return NB200_OK;
@@ -847,6 +848,35 @@ int nb200_final_linear(nb200_ctx *ctx, const float *hidden, float *logits_out) {
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(logits_out, ctx->logits, (size_t)V * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_detect_language(nb200_ctx *ctx, size_t window, const uint32_t *lang_tokens, size_t n_langs, uint32_t *token_out, float *probs_out) {
+    NB_TRY(check_decoder(ctx));
+    const nb200_config &c = ctx->cfg;
+    if (!ctx->has_tokens) return nb200_fail(ctx, NB200_NOT_LOADED, "special tokens not set (call nb200_set_tokens)");
+    if (!lang_tokens || n_langs == 0 || n_langs > (size_t)NB200_MAX_LANGS || !token_out || window >= (size_t)c.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "detect_language: n_langs=%zu window=%zu", n_langs, window);
+    if ((int)window >= ctx->n_resident) return nb200_fail(ctx, NB200_NOT_LOADED, "detect_language: window %zu has no resident audio features", window);
+    for (size_t i = 0; i < n_langs; ++i)
+        if (lang_tokens[i] >= (uint32_t)c.vocab_size) return nb200_fail(ctx, NB200_INVALID_ARG, "detect_language: token %u out of vocab", lang_tokens[i]);
+    // `decoder_forward([[sot]], audio_features, flush = true)` then `final_linear(ys[..1])` (model.rs:195-197)
+    NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
+    const int P = c.max_target_positions;
+    const int one = 1;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tokens + window * P, &ctx->tok.sot, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_len + window, &one, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lang, lang_tokens, n_langs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // the three sources above are pageable / stack memory
+    NB_TRY(decoder_step(ctx, (int)window, 1, 0, 1));
+    NB_TRY(decoder_language(ctx, (int)n_langs));
+    int best = -1;
+    const float *d_probs = (const float *)((const uint32_t *)ctx->d_lang + NB200_MAX_LANGS);
+    CUDA_TRY(ctx, cudaMemcpyAsync(&best, d_probs + NB200_MAX_LANGS, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (probs_out) CUDA_TRY(ctx, cudaMemcpyAsync(probs_out, d_probs, n_langs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (best < 0 || best >= (int)n_langs) return nb200_fail(ctx, NB200_CUDA_ERROR, "detect_language: no maximum (non-finite logits)");
+    *token_out = lang_tokens[best];
     return NB200_OK;
 }
 

@@ -138,6 +138,7 @@ struct nb200_ctx {
     int *d_len = nullptr, *d_last_ts = nullptr, *d_done = nullptr, *d_nsampled = nullptr;
     double *d_sumlp = nullptr;
     float *d_nospeech = nullptr;
+    void *d_lang = nullptr;      // detect_language scratch: [NB200_MAX_LANGS] u32 ids | [NB200_MAX_LANGS] f32 probs | i32 best
     void *d_sel_ws = nullptr;    // greedy select partials: [max_batch][32] float2 + [max_batch][32] SelCand
     float *d_attn_ws = nullptr;  // split-K decode attention partials [max_batch][heads][8][66]
     void *d_dyn = nullptr;  // DecodeDyn (decoder.cu): device-resident position / temperature / seed / token budget
@@ -225,6 +226,8 @@ int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int ran
 int decoder_select(nb200_ctx *ctx, int n_windows, int greedy);  // also advances the device-resident position
 int decoder_set_dyn(nb200_ctx *ctx, int pos, int max_new, float temperature, unsigned long long seed, int set_params);
 int decoder_nospeech(nb200_ctx *ctx, int n_windows);
+constexpr int NB200_MAX_LANGS = 1024;
+int decoder_language(nb200_ctx *ctx, int n_langs);  // softmax over logits[ids] of row 0, first-index argmax -> d_lang
 int decoder_init_state(nb200_ctx *ctx, int n_windows);
 // api.cu
 int encoder_run(nb200_ctx *ctx, int n_windows);

@@ -647,6 +647,42 @@ nospeech_kernel(const float *__restrict__ logits, int V, uint32_t no_speech, flo
     }
 }
 
+// `detect_language` (model.rs:198-207): softmax over the logits of the language tokens only, then the FIRST maximum in
+// `Language` order (a stable descending sort by total_cmp keeps the earlier of equal probabilities first)
+__global__ void __launch_bounds__(1024)
+language_kernel(const float *__restrict__ logits, const uint32_t *__restrict__ ids, int n, float *__restrict__ probs, int *__restrict__ best) {
+    __shared__ float red[32];
+    __shared__ int redi[32];
+    const int tid = threadIdx.x;
+    const float x = tid < n ? logits[ids[tid]] : -INFINITY;
+    const float mx = block_max(x, red);
+    const float e = tid < n ? expf(x - mx) : 0.f;
+    const float sum = block_sum(e, red);
+    const float p = e / sum;
+    if (tid < n) probs[tid] = p;
+    // arg-max of p with the lowest index winning ties
+    float bp = tid < n ? p : -1.f;
+    int bi = tid < n ? tid : 0x7fffffff;
+    for (int o = 16; o; o >>= 1) {
+        const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (op > bp || (op == bp && oi < bi)) { bp = op; bi = oi; }
+    }
+    __syncthreads();  // everyone is done reading red[] in block_sum
+    if ((tid & 31) == 0) { red[tid >> 5] = bp; redi[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid < 32) {
+        bp = red[tid];
+        bi = redi[tid];
+        for (int o = 16; o; o >>= 1) {
+            const float op = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (op > bp || (op == bp && oi < bi)) { bp = op; bi = oi; }
+        }
+        if (tid == 0) *best = bi;
+    }
+}
+
 __global__ void init_state_kernel(uint32_t *tokens, int max_pos, int *len, int *last_ts, int *done, int *nsampled, double *sumlp, float *nospeech,
                                   uint32_t t0, uint32_t t1, uint32_t t2, int plen) {
     const int b = blockIdx.x;
@@ -832,6 +868,16 @@ int decoder_step(nb200_ctx *ctx, int w0, int n_windows, int pos, int want_logits
 int decoder_nospeech(nb200_ctx *ctx, int n_windows) {
     KernelScope ks(ctx, NB200_K_DECODE_SELECT);
     nospeech_kernel<<<n_windows, 1024, 0, ctx->stream>>>(ctx->logits, ctx->cfg.vocab_size, ctx->tok.no_speech, ctx->d_nospeech, ctx->d_done, 0.6f);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+int decoder_language(nb200_ctx *ctx, int n_langs) {
+    KernelScope ks(ctx, NB200_K_DECODE_SELECT);
+    uint32_t *ids = (uint32_t *)ctx->d_lang;
+    float *probs = (float *)(ids + NB200_MAX_LANGS);
+    int *best = (int *)(probs + NB200_MAX_LANGS);
+    language_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->logits, ids, n_langs, probs, best);
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;
 }

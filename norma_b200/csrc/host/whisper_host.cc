@@ -30,6 +30,7 @@ std::vector<std::pair<size_t, size_t>> inclusive_boxed_by(const std::vector<uint
 
 WhisperModel::WhisperModel(Backend *backend, const nb200_special_tokens &tok, size_t max_chunk_len) : be_(backend), tok_(tok) {
     buf_.reserve(max_chunk_len);  // monolingual.rs:434
+    lang_ = tok.lang;             // LanguageState::ConstLang(lang_token), monolingual.rs:449
 }
 
 void WhisperModel::set_vocab(uint32_t id, const std::string &bytes) {
@@ -38,6 +39,7 @@ void WhisperModel::set_vocab(uint32_t id, const std::string &bytes) {
 }
 
 std::string WhisperModel::detokenize(const uint32_t *t, size_t n) const {
+    if (has_tokenizer_) return tokenizer_.decode(t, n, true);  // self.tokenizer.decode(.., true), model.rs:147
     std::string s;
     for (size_t i = 0; i < n; ++i) {
         if (t[i] >= tok_.eot) continue;  // skip_special_tokens: every Whisper special id is >= <|endoftext|>
@@ -47,7 +49,17 @@ std::string WhisperModel::detokenize(const uint32_t *t, size_t n) const {
 }
 
 int WhisperModel::decode_with_fallback(bool *some, DecodingResult *out) {
-    // model.rs:168 happened in the caller (encode); language detection (model.rs:170-173) is multilingual-only
+    // model.rs:168 happened in the caller (encode)
+    if (detect_ && !lang_set_) {                                                           // model.rs:170 `self.lang.is_none()`
+        uint32_t lang = UINT32_MAX;
+        int st = be_->detect_language(lang_tokens_, &lang);                                // model.rs:171
+        ++n_detects;
+        if (st != NB200_OK) { err_ = be_->last_error(); return st; }
+        lang_ = lang;                                                                      // model.rs:172
+        lang_set_ = true;
+        st = be_->set_language(lang);
+        if (st != NB200_OK) { err_ = be_->last_error(); return st; }
+    }
     for (double t : TEMPERATURES) {                                                        // model.rs:175
         DecodingResult dr;
         int st = be_->decode(t, &dr);                                                      // model.rs:176
@@ -120,7 +132,8 @@ int WhisperModel::transcribe(const float *data, size_t n, bool final_chunk, std:
         }
     }
     if (final_chunk) {                                                                     // model.rs:153-156
-        int st = be_->reset_kv_cache();
+        if (detect_) { lang_set_ = false; lang_ = UINT32_MAX; }                            // model.rs:154 `self.lang.clear()`
+        int st = be_->reset_kv_cache();                                                    // model.rs:155
         if (st != NB200_OK) { err_ = be_->last_error(); return st; }
     }
     if (text) *text = res;
@@ -151,11 +164,34 @@ int Nb200Backend::decode(double t, DecodingResult *out) {
     return NB200_OK;
 }
 
+int Nb200Backend::detect_language(const std::vector<uint32_t> &lang_tokens, uint32_t *token) {
+    return nb200_detect_language(ctx_, 0, lang_tokens.data(), lang_tokens.size(), token, nullptr);
+}
+
+int Nb200Backend::set_language(uint32_t token) {
+    tok_.lang = token;
+    return nb200_set_tokens(ctx_, &tok_);
+}
+
 int Nb200Backend::reset_kv_cache() { return nb200_reset_kv_cache(ctx_); }
 std::string Nb200Backend::last_error() { return nb200_last_error(ctx_); }
 
 int ScriptedBackend::encode(const float *, size_t n) {
     encode_lens.push_back(n);
+    return NB200_OK;
+}
+
+int ScriptedBackend::detect_language(const std::vector<uint32_t> &lang_tokens, uint32_t *token) {
+    if (language_script.empty()) {
+        err_ = "scripted backend ran out of detected languages";
+        return NB200_INVALID_ARG;
+    }
+    *token = language_script.front();
+    language_script.pop_front();
+    if (std::find(lang_tokens.begin(), lang_tokens.end(), *token) == lang_tokens.end()) {
+        err_ = "scripted language is not one of the language tokens";
+        return NB200_INVALID_ARG;
+    }
     return NB200_OK;
 }
 
@@ -176,19 +212,12 @@ int ScriptedBackend::decode(double t, DecodingResult *out) {
 // ---------------------------------------------------------------------------------------------------------
 // C ABI (declared in include/norma_b200.h)
 // ---------------------------------------------------------------------------------------------------------
-struct nb200_model {
-    nb200host::Backend *backend = nullptr;
-    nb200host::ScriptedBackend *scripted = nullptr;
-    nb200host::WhisperModel *model = nullptr;
-    std::string err;
-};
-
 extern "C" {
 
 int nb200_model_create(nb200_ctx *ctx, const nb200_special_tokens *tok, size_t max_chunk_len, uint64_t seed, nb200_model **out) {
     if (!tok || !out) return NB200_INVALID_ARG;
     nb200_model *m = new nb200_model();
-    if (ctx) m->backend = new nb200host::Nb200Backend(ctx, seed);
+    if (ctx) m->backend = new nb200host::Nb200Backend(ctx, *tok, seed);
     else m->backend = m->scripted = new nb200host::ScriptedBackend();
     m->model = new nb200host::WhisperModel(m->backend, *tok, max_chunk_len);
     *out = m;
@@ -255,6 +284,27 @@ int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_encodes, size_
     if (n_encodes) *n_encodes = m->model->n_encodes;
     if (n_decodes) *n_decodes = m->model->n_decodes;
     if (n_resets) *n_resets = m->scripted ? (size_t)m->scripted->resets : 0;
+    return NB200_OK;
+}
+
+int nb200_model_set_language_detection(nb200_model *m, const uint32_t *lang_tokens, size_t n) {
+    if (!m || !lang_tokens || n == 0) return NB200_INVALID_ARG;
+    m->model->set_language_detection(std::vector<uint32_t>(lang_tokens, lang_tokens + n));
+    return m->backend->set_language(UINT32_MAX);
+}
+
+int nb200_model_language(nb200_model *m, uint32_t *token, size_t *n_detects) {
+    if (!m) return NB200_INVALID_ARG;
+    uint32_t t = UINT32_MAX;
+    const bool some = m->model->language(&t);
+    if (token) *token = some ? t : UINT32_MAX;
+    if (n_detects) *n_detects = m->model->n_detects;
+    return NB200_OK;
+}
+
+int nb200_model_script_push_language(nb200_model *m, uint32_t token) {
+    if (!m || !m->scripted) return NB200_INVALID_ARG;
+    m->scripted->language_script.push_back(token);
     return NB200_OK;
 }
 

@@ -2,6 +2,8 @@
 // toolchain is absent from this image (INTEGRATION.md shows the Rust it stands in for).  Mirrors, line by line:
 //   Model::transcribe            /root/reference/src/models/whisper/model.rs:55-160
 //   Model::decode_with_fallback  /root/reference/src/models/whisper/model.rs:164-191
+//   Model::detect_language       /root/reference/src/models/whisper/model.rs:194-210
+//   LanguageState                /root/reference/src/models/whisper/model.rs:392-440
 //   SliceExt::inclusive_boxed_by /root/reference/src/utils.rs:1-76
 // The device work (pcm_to_mel, encoder, decode) goes through a `Backend`; `Nb200Backend` calls the C ABI,
 // `ScriptedBackend` replays canned DecodingResults so the buffering / seek / fallback logic is testable without a GPU.
@@ -13,6 +15,7 @@
 #include <vector>
 
 #include "../../../include/norma_b200.h"
+#include "loader.h"
 
 namespace nb200host {
 
@@ -36,20 +39,27 @@ struct Backend {
     virtual int encode(const float *pcm, size_t n) = 0;
     // Model::decode(audio_features, t)  (model.rs:279-390)
     virtual int decode(double t, DecodingResult *out) = 0;
+    // Model::detect_language(audio_features): id of the most probable of `lang_tokens`  (model.rs:194-210)
+    virtual int detect_language(const std::vector<uint32_t> &lang_tokens, uint32_t *token) = 0;
+    // the language token `decode` puts in its prompt (model.rs:286-288); UINT32_MAX = none
+    virtual int set_language(uint32_t token) = 0;
     virtual int reset_kv_cache() = 0;
     virtual std::string last_error() = 0;
 };
 
 class Nb200Backend : public Backend {
 public:
-    Nb200Backend(nb200_ctx *ctx, uint64_t seed) : ctx_(ctx), seed_(seed) {}
+    Nb200Backend(nb200_ctx *ctx, const nb200_special_tokens &tok, uint64_t seed) : ctx_(ctx), tok_(tok), seed_(seed) {}
     int encode(const float *pcm, size_t n) override;
     int decode(double t, DecodingResult *out) override;
+    int detect_language(const std::vector<uint32_t> &lang_tokens, uint32_t *token) override;
+    int set_language(uint32_t token) override;
     int reset_kv_cache() override;
     std::string last_error() override;
 
 private:
     nb200_ctx *ctx_;
+    nb200_special_tokens tok_;
     uint64_t seed_, draws_ = 0;
 };
 
@@ -57,9 +67,13 @@ class ScriptedBackend : public Backend {
 public:
     int encode(const float *pcm, size_t n) override;
     int decode(double t, DecodingResult *out) override;
+    int detect_language(const std::vector<uint32_t> &lang_tokens, uint32_t *token) override;
+    int set_language(uint32_t token) override { languages_set.push_back(token); return NB200_OK; }
     int reset_kv_cache() override { ++resets; return NB200_OK; }
     std::string last_error() override { return err_; }
     std::deque<DecodingResult> script;
+    std::deque<uint32_t> language_script;   // results of successive detect_language calls
+    std::vector<uint32_t> languages_set;    // every set_language call
     std::vector<size_t> encode_lens;   // slice length of every encode call
     std::vector<double> decode_temps;  // temperature of every decode call
     int resets = 0;
@@ -79,6 +93,12 @@ public:
     int transcribe(const float *data, size_t n, bool final_chunk, std::string *text, std::vector<std::vector<uint32_t>> *segments);
     int decode_with_fallback(bool *some, DecodingResult *out);
     void set_vocab(uint32_t id, const std::string &bytes);
+    void set_tokenizer(const Tokenizer &t) { tokenizer_ = t; has_tokenizer_ = true; }
+    // LanguageState::Detect { language_token: None, language_tokens_tensor } (multilingual.rs:319-322); the default is
+    // LanguageState::ConstLang(tok.lang) (monolingual.rs:449)
+    void set_language_detection(const std::vector<uint32_t> &lang_tokens) { detect_ = true; lang_tokens_ = lang_tokens; lang_set_ = false; }
+    bool language(uint32_t *token) const { *token = lang_; return !detect_ || lang_set_; }  // LanguageState::language_token
+    size_t n_detects = 0;
     size_t buffered() const { return buf_.size(); }
     std::string last_error() const { return err_; }
     size_t n_encodes = 0, n_decodes = 0;
@@ -89,7 +109,19 @@ private:
     nb200_special_tokens tok_;
     std::vector<float> buf_;
     std::vector<std::string> vocab_;
+    Tokenizer tokenizer_;
+    bool has_tokenizer_ = false;
+    bool detect_ = false, lang_set_ = false;  // LanguageState (model.rs:392-440)
+    uint32_t lang_ = UINT32_MAX;
+    std::vector<uint32_t> lang_tokens_;
     std::string err_;
 };
 
 }  // namespace nb200host
+
+struct nb200_model {
+    nb200host::Backend *backend = nullptr;
+    nb200host::ScriptedBackend *scripted = nullptr;
+    nb200host::WhisperModel *model = nullptr;
+    std::string err;
+};

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnorma_b200.so")
 
 NB200_OK = 0
-STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH"}
+STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH", 7: "IO_ERROR", 8: "PARSE_ERROR", 9: "NOT_FOUND"}
+TASKS = {"transcribe": 0, "translate": 1}
 DTYPES = {"f32": 0, "bf16": 1, "f16": 2, "f64": 3, "u8": 4, "u32": 5}
 KERNEL_CLASSES = ["mel", "mel_norm", "gemm", "attn", "layernorm", "decode_gemv", "decode_attn", "decode_select", "misc"]
 Q = dict(n_frames=0, enc_len=1, d_model=2, vocab=3, max_batch=4, kernel_launches=5, device_bytes=6, compute_dtype=7, max_target_positions=8)
@@ -30,6 +31,10 @@ SYMBOLS = [
     "nb200_model_state", "nb200_model_script_push", "nb200_model_script_log",
     "nb200_stream_reset", "nb200_stream_push", "nb200_stream_drain", "nb200_stream_features",
     "nb200_transcode_submit", "nb200_transcode_collect",
+    "nb200_detect_language", "nb200_model_set_language_detection", "nb200_model_language", "nb200_model_script_push_language",
+    "nb200_config_from_file", "nb200_mel_filters", "nb200_tokenizer_from_file", "nb200_tokenizer_destroy", "nb200_tokenizer_token_to_id",
+    "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read",
+    "nb200_model_set_tokenizer", "nb200_model_from_files",
 ]
 
 
@@ -110,6 +115,22 @@ def load_library() -> C.CDLL:
         "nb200_stream_push": ([p, f32p, sz], i),
         "nb200_stream_drain": ([p, sz], i),
         "nb200_stream_features": ([p, i, f32p, f32p], i),
+        "nb200_detect_language": ([p, sz, u32p, sz, u32p, f32p], i),
+        "nb200_model_set_language_detection": ([p, u32p, sz], i),
+        "nb200_model_language": ([p, u32p, C.POINTER(sz)], i),
+        "nb200_model_script_push_language": ([p, C.c_uint32], i),
+        "nb200_config_from_file": ([C.c_char_p, C.POINTER(Config), u32p, sz, C.POINTER(sz)], i),
+        "nb200_mel_filters": ([i, f32p], i),
+        "nb200_tokenizer_from_file": ([C.c_char_p, C.POINTER(p)], i),
+        "nb200_tokenizer_destroy": ([p], None),
+        "nb200_tokenizer_token_to_id": ([p, C.c_char_p, u32p], i),
+        "nb200_tokenizer_decode": ([p, u32p, sz, i, C.c_char_p, sz, C.POINTER(sz)], i),
+        "nb200_tokenizer_special_tokens": ([p, C.c_char_p, i, C.POINTER(SpecialTokens)], i),
+        "nb200_tokenizer_language_tokens": ([p, u32p], i),
+        "nb200_load_safetensors": ([p, C.c_char_p, C.POINTER(sz)], i),
+        "nb200_safetensors_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i)], i),
+        "nb200_model_set_tokenizer": ([p, p], i),
+        "nb200_model_from_files": ([i, C.c_char_p, C.c_char_p, C.c_char_p, i, C.c_char_p, i, sz, C.c_uint64, C.POINTER(p), C.POINTER(p)], i),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export it
@@ -134,21 +155,103 @@ def bf16_round(a: np.ndarray) -> np.ndarray:
     return (f32_to_bf16_bits(a).astype(np.uint32) << 16).view(np.float32)
 
 
+def _ck_global(lib, st: int):
+    if st != NB200_OK:
+        raise Nb200Error(st, (lib.nb200_last_error(None) or b"").decode())
+
+
+def config_from_file(path: str):
+    """`serde_json::from_str::<Config>` (monolingual.rs:347): returns (config dict, suppress_tokens list)."""
+    lib = load_library()
+    c = Config()
+    n = C.c_size_t()
+    sup = np.zeros(1 << 16, np.uint32)
+    _ck_global(lib, lib.nb200_config_from_file(os.fsencode(path), C.byref(c), sup.ctypes.data_as(C.POINTER(C.c_uint32)), sup.size, C.byref(n)))
+    cfg = {k: int(getattr(c, k)) for k, _ in Config._fields_ if k != "max_batch"}
+    return cfg, sup[: n.value].tolist()
+
+
+def mel_filters(n_mel: int) -> np.ndarray:
+    lib = load_library()
+    out = np.empty((max(n_mel, 1), 201), np.float32)
+    _ck_global(lib, lib.nb200_mel_filters(n_mel, _f32p(out)))
+    return out
+
+
+def safetensors_read(path: str, name: str) -> np.ndarray:
+    """One tensor of a .safetensors file converted to f32 (what `VarBuilder::from_mmaped_safetensors(.., F32, ..)` yields)."""
+    lib = load_library()
+    shape = (C.c_int64 * 8)()
+    rank = C.c_int()
+    _ck_global(lib, lib.nb200_safetensors_read(os.fsencode(path), name.encode(), None, 0, shape, C.byref(rank)))
+    shp = tuple(int(shape[k]) for k in range(rank.value))
+    out = np.empty(shp, np.float32)
+    _ck_global(lib, lib.nb200_safetensors_read(os.fsencode(path), name.encode(), _f32p(out), out.size, None, None))
+    return out
+
+
+class Tokenizer:
+    """nb200_tokenizer: `tokenizers::Tokenizer::from_file` + token_to_id + decode (monolingual.rs:348; model.rs:147)."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _ck_global(self.lib, self.lib.nb200_tokenizer_from_file(os.fsencode(path), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nb200_tokenizer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def token_to_id(self, token: str) -> int:
+        v = C.c_uint32()
+        _ck_global(self.lib, self.lib.nb200_tokenizer_token_to_id(self.h, token.encode(), C.byref(v)))
+        return v.value
+
+    def decode(self, ids: Sequence[int], skip_special_tokens: bool = True) -> str:
+        t = np.ascontiguousarray(np.asarray(list(ids), np.uint32))
+        n = C.c_size_t()
+        ptr = t.ctypes.data_as(C.POINTER(C.c_uint32))
+        _ck_global(self.lib, self.lib.nb200_tokenizer_decode(self.h, ptr, t.size, int(skip_special_tokens), None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        _ck_global(self.lib, self.lib.nb200_tokenizer_decode(self.h, ptr, t.size, int(skip_special_tokens), buf, n.value + 1, None))
+        return buf.raw[: n.value].decode("utf-8")
+
+    def special_tokens(self, language_token: Optional[str], task: str = "transcribe") -> Dict[str, int]:
+        st = SpecialTokens()
+        lt = None if language_token is None else language_token.encode()
+        _ck_global(self.lib, self.lib.nb200_tokenizer_special_tokens(self.h, lt, TASKS[task], C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in SpecialTokens._fields_}
+
+    def language_tokens(self):
+        out = np.zeros(99, np.uint32)
+        _ck_global(self.lib, self.lib.nb200_tokenizer_language_tokens(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out.tolist()
+
+
 class Context:
     """One nb200_ctx: one GPU ordinal, one stream.  Mirrors what norma's whisper `Model` owns
     (/root/reference/src/models/whisper/model.rs:16-42) on the device side."""
 
-    def __init__(self, cfg: Dict[str, int], ordinal: int = 0, compute: str = "bf16", max_batch: int = 1):
+    def __init__(self, cfg: Dict[str, int], ordinal: int = 0, compute: str = "bf16", max_batch: int = 1, handle=None):
         self.lib = load_library()
         self.cfg = dict(cfg)
         self.max_batch = max_batch
         self.compute = compute
-        c = Config(**{k: int(cfg[k]) for k, _ in Config._fields_ if k != "max_batch"}, max_batch=max_batch)
-        h = C.c_void_p()
-        st = self.lib.nb200_create(ordinal, C.byref(c), DTYPES[compute], C.byref(h))
-        if st != NB200_OK:
-            raise Nb200Error(st, (self.lib.nb200_last_error(None) or b"").decode())
-        self.h = h
+        if handle is None:
+            c = Config(**{k: int(cfg[k]) for k, _ in Config._fields_ if k != "max_batch"}, max_batch=max_batch)
+            handle = C.c_void_p()
+            st = self.lib.nb200_create(ordinal, C.byref(c), DTYPES[compute], C.byref(handle))
+            if st != NB200_OK:
+                raise Nb200Error(st, (self.lib.nb200_last_error(None) or b"").decode())
+        self.h = handle  # handle != None: adopt a ctx made by nb200_model_from_files
         self.d = cfg["d_model"]
         self.n_mel = cfg["num_mel_bins"]
         self.V = cfg["vocab_size"]
@@ -192,6 +295,14 @@ class Context:
             raise TypeError(f"unsupported dtype {a.dtype} for {name}")
         shape = (C.c_int64 * a.ndim)(*a.shape)
         self._ck(self.lib.nb200_load_tensor(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), dt, shape, a.ndim))
+
+    def load_safetensors(self, path: str, finalize: bool = True) -> int:
+        """`VarBuilder::from_mmaped_safetensors` + `Whisper::load` (monolingual.rs:371-373)."""
+        n = C.c_size_t()
+        self._ck(self.lib.nb200_load_safetensors(self.h, os.fsencode(path), C.byref(n)))
+        if finalize:
+            self._ck(self.lib.nb200_finalize_weights(self.h))
+        return n.value
 
     def load_weights(self, weights: Dict[str, object]):
         for k, v in weights.items():
@@ -320,6 +431,14 @@ class Context:
 
     def reset_kv_cache(self):
         self._ck(self.lib.nb200_reset_kv_cache(self.h))
+
+    def detect_language(self, lang_tokens: Sequence[int], window: int = 0):
+        """`Model::detect_language` (model.rs:194-210): returns (token id, probabilities over lang_tokens)."""
+        t = np.ascontiguousarray(np.asarray(list(lang_tokens), np.uint32))
+        probs = np.empty(t.size, np.float32)
+        tok = C.c_uint32()
+        self._ck(self.lib.nb200_detect_language(self.h, window, t.ctypes.data_as(C.POINTER(C.c_uint32)), t.size, C.byref(tok), _f32p(probs)))
+        return tok.value, probs
 
     def decode(self, n_windows: int = 1, temperature: float = 0.0, seed: int = 0, max_new_tokens: int = 0):
         toks = np.zeros((n_windows, self.P), np.uint32)

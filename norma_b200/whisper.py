@@ -3,11 +3,16 @@
   SelectedDevice                      /root/reference/src/models/mod.rs:38-55
   CommonModelParams                   /root/reference/src/models/mod.rs:57-117
   monolingual.ModelType / Definition  /root/reference/src/models/whisper/monolingual.rs:32-174
+  multilingual.ModelType / Task / Definition
+                                      /root/reference/src/models/whisper/multilingual.rs:16-175
+  Language                            /root/reference/src/models/whisper/languages.rs:7-222
   Model.transcribe(data, final_chunk) /root/reference/src/models/whisper/model.rs:55-160 (implemented in C++,
                                       norma_b200/csrc/host/whisper_host.cc, reached through nb200_model_*)
 
-What is NOT mirrored (out of scope): hf-hub download, tokenizer.json parsing, the Transcriber thread and
-cpal capture.  `Definition.try_to_model` therefore takes the weights / filters / vocabulary from the caller.
+What is NOT mirrored (out of scope): the hf-hub download, the Transcriber thread and cpal capture.
+`Definition.blocking_try_to_model_from_files` is `blocking_try_to_model` from the point where the three checkpoint
+files are on disk (config.json, tokenizer.json, model.safetensors; parsed by norma_b200/csrc/host/loader.cc);
+`Definition.blocking_try_to_model` takes weights / vocabulary from the caller instead (synthetic checkpoints).
 """
 from __future__ import annotations
 
@@ -77,6 +82,97 @@ class CommonModelParams:
         self._string_buffer_size = max(n, MIN_STRING_BUF_SIZE)
 
 
+LANGUAGE_CODES = (
+    "en zh de es ru ko fr ja pt tr pl ca nl ar sv it id hi fi vi he uk el ms cs ro da hu ta no th ur hr bg lt la mi ml cy sk te fa lv bn "
+    "sr az sl kn et mk br eu is hy ne mn bs kk sq sw gl mr pa si km sn yo so af oc ka be tg sd gu am yi lo uz fo ht ps tk nn mt sa lb my "
+    "bo tl mg as tt haw ln ha ba jw su").split()
+
+
+@dataclass(frozen=True)
+class Language:
+    """whisper::Language (languages.rs:7-107): the 99 variants in declaration order; `index` is the position."""
+    index: int
+
+    @staticmethod
+    def from_code(code: str) -> "Language":
+        return Language(LANGUAGE_CODES.index(code))
+
+    @staticmethod
+    def iter():
+        return [Language(i) for i in range(len(LANGUAGE_CODES))]
+
+    def code(self) -> str:
+        return LANGUAGE_CODES[self.index]
+
+    def token(self) -> str:  # languages.rs:120-222
+        return f"<|{self.code()}|>"
+
+
+Language.English = Language(0)
+
+
+class Task(enum.Enum):
+    """multilingual::Task (multilingual.rs:16-25)"""
+    Transcribe = "transcribe"
+    Translate = "translate"
+
+
+class MultilingualModelType(enum.Enum):
+    """multilingual::ModelType (multilingual.rs:47-116): (hub id, revision, architecture shape, vocab version)"""
+    QuantizedTiny = ("lmz/candle-whisper", "main", "tiny", "V1")
+    Tiny = ("openai/whisper-tiny", "main", "tiny", "V1")
+    Base = ("openai/whisper-base", "refs/pr/22", "base", "V1")
+    Small = ("openai/whisper-small", "main", "small", "V1")
+    Medium = ("openai/whisper-medium", "main", "medium", "V1")
+    Large = ("openai/whisper-large", "refs/pr/36", "large", "V1")
+    LargeV2 = ("openai/whisper-large-v2", "refs/pr/57", "large-v2", "V1")
+    LargeV3 = ("openai/whisper-large-v3", "main", "large-v3", "V2")
+
+    @classmethod
+    def default(cls):
+        return cls.Medium  # #[default], multilingual.rs:53-54
+
+    def id(self) -> str:
+        return self.value[0]
+
+    def rev(self) -> str:
+        return self.value[1]
+
+    def shape(self) -> str:
+        return self.value[2]
+
+    def vocab_version(self) -> str:
+        return self.value[3]
+
+    def quantized_ext(self) -> Optional[str]:
+        return "tiny" if self is MultilingualModelType.QuantizedTiny else None
+
+
+@dataclass(frozen=True)
+class MultiAsMono:
+    """monolingual::ModelType::MultiAsMono { model, lang } (monolingual.rs:42-45): a multilingual checkpoint pinned to one language."""
+    model: MultilingualModelType
+    lang: Language
+
+    def id(self) -> str:
+        return self.model.id()
+
+    def rev(self) -> str:
+        return self.model.rev()
+
+    def shape(self) -> str:
+        return self.model.shape()
+
+    def vocab_version(self) -> str:
+        return self.model.vocab_version()
+
+    def quantized_ext(self) -> Optional[str]:
+        return self.model.quantized_ext()
+
+    def language(self) -> Language:
+        return self.lang
+
+
 class ModelType(enum.Enum):
     """monolingual::ModelType (monolingual.rs:32-111): (hub id, revision, architecture shape, vocab version)"""
     QuantizedTinyEn = ("lmz/candle-whisper", "main", "tiny.en", "EnV1")
@@ -107,16 +203,23 @@ class ModelType(enum.Enum):
     def quantized_ext(self) -> Optional[str]:
         return "tiny-en" if self is ModelType.QuantizedTinyEn else None
 
+    def language(self) -> Language:
+        return Language.English  # monolingual.rs:85-96
+
+
+ModelType.MultiAsMono = MultiAsMono
+
 
 class Definition:
-    """monolingual::Definition (monolingual.rs:116-174)"""
+    """monolingual::Definition (monolingual.rs:116-174).  `task` / `detect` carry multilingual::Definition
+    (multilingual.rs:108-175) on the same class: see `MultilingualDefinition`."""
 
-    def __init__(self, model: ModelType, device: SelectedDevice):
-        self.model, self.device = model, device
-        self.common_params = CommonModelParams(SAMPLE_RATE * 25, 3, 3)  # monolingual.rs:128
+    def __init__(self, model, device: SelectedDevice, task: Task = Task.Transcribe, detect: bool = False):
+        self.model, self.device, self.task, self.detect = model, device, task, detect
+        self.common_params = CommonModelParams(SAMPLE_RATE * 25, 3, 3)  # monolingual.rs:128, multilingual.rs:126
 
     @staticmethod
-    def new(model: ModelType, device: SelectedDevice) -> "Definition":
+    def new(model, device: SelectedDevice) -> "Definition":
         return Definition(model, device)
 
     def set_responsiveness(self, period_ms: int):
@@ -142,20 +245,60 @@ class Definition:
         ctx = ffi.Context(cfg, ordinal=self.device.ordinal, compute=compute, max_batch=1)
         ctx.set_mel_filters(filters.mel_filters(cfg["num_mel_bins"]))  # Error::MelBins for anything but 80 | 128
         ctx.load_weights(weights)
-        tok = synth.special_tokens(cfg["vocab_size"])
+        tok = synth.special_tokens(cfg["vocab_size"], task=self.task.value, lang=None if self.detect else self.model.language().index)
         ctx.set_tokens(**tok)
         ctx.set_suppress(suppress_tokens)
-        return Model(ctx, tok, self.common_params.max_chunk_len(), vocab, seed)
+        m = Model(ctx, tok, self.common_params.max_chunk_len(), vocab, seed)
+        if self.detect:  # LanguageState::Detect (multilingual.rs:319-322)
+            m.set_language_detection(synth.language_tokens(cfg["vocab_size"]))
+        return m
+
+    def blocking_try_to_model_from_files(self, config_json: str, tokenizer_json: str, safetensors: str, compute: str = "bf16",
+                                         seed: int = 0) -> "Model":
+        """monolingual.rs:347-451 / multilingual.rs:225-323: everything `blocking_try_to_model` does once hf-hub has put the
+        three files on disk (parsing, upload, token-id lookups, masks), done natively by nb200_model_from_files."""
+        if self.device.kind != "cuda":
+            raise WhisperError("this build only implements SelectedDevice::Cuda(ord) (sm_100a, no CPU fallback)")
+        if self.model.quantized_ext() is not None:
+            raise WhisperError("quantized (q8_0) checkpoints are out of scope for the B200 path")
+        import os
+
+        lib = ffi.load_library()
+        ch, mh = C.c_void_p(), C.c_void_p()
+        lang = None if self.detect else self.model.language().token().encode()
+        st = lib.nb200_model_from_files(self.device.ordinal, os.fsencode(config_json), os.fsencode(tokenizer_json), os.fsencode(safetensors),
+                                        ffi.DTYPES[compute], lang, ffi.TASKS[self.task.value], self.common_params.max_chunk_len(), seed,
+                                        C.byref(ch), C.byref(mh))
+        if st != 0:
+            raise ffi.Nb200Error(st, (lib.nb200_last_error(None) or b"").decode())
+        cfg, _ = ffi.config_from_file(config_json)
+        ctx = ffi.Context(cfg, ordinal=self.device.ordinal, compute=compute, max_batch=1, handle=ch)
+        return Model(ctx, None, 0, handle=mh)
+
+
+class MultilingualDefinition(Definition):
+    """multilingual::Definition::new(model, device, task) (multilingual.rs:108-127): language detected per transcription."""
+
+    def __init__(self, model: MultilingualModelType, device: SelectedDevice, task: Task = Task.Transcribe):
+        super().__init__(model, device, task, detect=True)
+
+    @staticmethod
+    def new(model: MultilingualModelType, device: SelectedDevice, task: Task = Task.Transcribe) -> "MultilingualDefinition":
+        return MultilingualDefinition(model, device, task)
 
 
 class Model:
     """whisper::Model (model.rs:16-160): `Data = f32`, `SAMPLE_RATE = 16_000`."""
     SAMPLE_RATE = SAMPLE_RATE
 
-    def __init__(self, ctx: Optional[ffi.Context], tok: Dict[str, int], max_chunk_len: int, vocab: Optional[Dict[int, bytes]] = None,
-                 seed: int = 0):
+    def __init__(self, ctx: Optional[ffi.Context], tok: Optional[Dict[str, int]], max_chunk_len: int, vocab: Optional[Dict[int, bytes]] = None,
+                 seed: int = 0, handle=None):
         self.lib = ffi.load_library()
         self.ctx = ctx
+        self._owns_ctx = handle is not None
+        if handle is not None:  # adopt an nb200_model made by nb200_model_from_files
+            self.h = handle
+            return
         t = ffi.SpecialTokens(tok["sot"], tok["eot"], tok["task"], 0xFFFFFFFF if tok.get("lang") is None else tok["lang"], tok["no_speech"],
                               tok["no_timestamps"], tok["ts_zero"], tok["ts_one"])
         h = C.c_void_p()
@@ -170,6 +313,28 @@ class Model:
         if getattr(self, "h", None):
             self.lib.nb200_model_destroy(self.h)
             self.h = None
+        if getattr(self, "_owns_ctx", False) and self.ctx is not None:
+            self.ctx.close()
+
+    def set_tokenizer(self, tokenizer: "ffi.Tokenizer"):
+        self.lib.nb200_model_set_tokenizer(self.h, tokenizer.h)
+
+    def set_language_detection(self, lang_tokens: Sequence[int]):
+        t = np.ascontiguousarray(np.asarray(list(lang_tokens), np.uint32))
+        st = self.lib.nb200_model_set_language_detection(self.h, t.ctypes.data_as(C.POINTER(C.c_uint32)), t.size)
+        if st != 0:
+            raise ffi.Nb200Error(st, (self.lib.nb200_model_last_error(self.h) or b"").decode())
+
+    def language(self) -> Tuple[Optional[int], int]:
+        """-> (`LanguageState::language_token()`, number of detect_language calls so far)"""
+        t, n = C.c_uint32(), C.c_size_t()
+        self.lib.nb200_model_language(self.h, C.byref(t), C.byref(n))
+        return (None if t.value == 0xFFFFFFFF else t.value), n.value
+
+    def script_push_language(self, token: int):
+        st = self.lib.nb200_model_script_push_language(self.h, token)
+        if st != 0:
+            raise ffi.Nb200Error(st, "script_push_language on a non-scripted model")
 
     def __del__(self):
         try:

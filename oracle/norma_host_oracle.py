@@ -4,6 +4,7 @@ Python restatement of the host logic of norma's whisper `Model` (buffering, 30 s
 timestamp segmentation, seek), statement by statement from
   /root/reference/src/models/whisper/model.rs:55-160   Model::transcribe
   /root/reference/src/models/whisper/model.rs:164-191  Model::decode_with_fallback
+  /root/reference/src/models/whisper/model.rs:392-440  LanguageState (Detect / ConstLang)
   /root/reference/src/utils.rs:1-76                     SliceExt::inclusive_boxed_by
 `encode` / `decode` are callbacks so the same restatement runs over scripted results (CPU tests of the C++ mirror) or
 over the model oracle.  PARITY UNPINNED: the reference's only tests of this code are two `#[ignore]`d microphone tests
@@ -36,13 +37,18 @@ def inclusive_boxed_by(v: List[int], pred: Callable[[int], bool]):
 
 
 class HostModelOracle:
-    def __init__(self, encode, decode, reset_kv_cache, no_timestamps: int, eot: int, detok=None):
+    def __init__(self, encode, decode, reset_kv_cache, no_timestamps: int, eot: int, detok=None, detect_language=None, const_lang=None):
         self.encode, self.decode, self.reset_kv_cache = encode, decode, reset_kv_cache
         self.nts, self.eot = no_timestamps, eot
         self.detok = detok or (lambda toks: "")
         self.buf: List[float] = []
+        # LanguageState: Detect { language_token: None, .. } when a detector is given (multilingual.rs:319-322), else ConstLang
+        self.detect_language = detect_language
+        self.language_token: Optional[int] = None if detect_language else const_lang
 
     def decode_with_fallback(self):
+        if self.detect_language is not None and self.language_token is None:     # model.rs:170 `self.lang.is_none()`
+            self.language_token = self.detect_language()                         # model.rs:171-172
         for t in TEMPERATURES:                                                   # model.rs:175
             dr = self.decode(t)                                                  # (tokens, avg_logprob, no_speech_prob)
             compression_ratio = float("nan")
@@ -85,5 +91,7 @@ class HostModelOracle:
                 segs.append(seg)
                 res += self.detok(seg[1:-1])                                     # model.rs:147-149
         if final_chunk:
+            if self.detect_language is not None:
+                self.language_token = None                                       # model.rs:154 `self.lang.clear()`
             self.reset_kv_cache()                                                # model.rs:153-156
         return res, segs

@@ -408,3 +408,15 @@ class GreedyDecoder:
         while len(tokens) >= 2 and tokens[-2] > st.no_timestamps:
             del tokens[-2]
         return DecodingResult(tokens, avg_logprob, no_speech_prob, margins=margins)
+
+
+@torch.no_grad()
+def detect_language(model: WhisperOracle, sot: int, language_tokens: List[int], audio_features: torch.Tensor):
+    """norma `Model::detect_language` (/root/reference/src/models/whisper/model.rs:194-210): one decoder pass over [[sot]] with
+    flush = true, the logits of the language tokens only, softmax over those, then a STABLE descending sort by total_cmp — so the
+    first of equal probabilities wins.  Returns (token id, probabilities in `language_tokens` order)."""
+    ys = model.decoder_forward(torch.tensor([[sot]]), audio_features, True)
+    logits = model.final_linear(ys[:1, :1])[0, 0]
+    probs = torch.softmax(logits.float()[torch.tensor(language_tokens)], -1)
+    order = sorted(range(len(language_tokens)), key=lambda i: -float(probs[i]))  # Python's sort is stable, like slice::sort_by
+    return language_tokens[order[0]], probs.numpy()

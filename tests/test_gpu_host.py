@@ -112,3 +112,180 @@ def test_temperature_sampler_distribution_and_determinism(lib):
     assert a == b  # explicit seed: reproducible (the reference seeds from entropy, monolingual.rs:439)
     assert any(ctx.decode(1, 0.7, seed=s, max_new_tokens=6) != a for s in range(6, 12))
     ctx.close()
+
+
+# ---- multilingual path: detect_language, Task::Translate, MultiAsMono ---------------------------------
+def _multilingual_ctx(c, w, compute, tok):
+    ctx = ffi.Context(c, compute=compute, max_batch=1)
+    ctx.set_mel_filters(filters.mel_filters(c["num_mel_bins"]))
+    ctx.load_weights(w)
+    ctx.set_tokens(**tok)
+    return ctx
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+def test_detect_language_matches_oracle(lib, compute):
+    """Random-init multilingual tiny: the 99 probabilities agree with the oracle and so does the arg-max when its margin is clear."""
+    from oracle.whisper_oracle import detect_language
+
+    c = synth.model_config("tiny")
+    w = synth.synth_weights(c, seed=1)
+    tok = synth.special_tokens(c["vocab_size"], lang=None)
+    langs = synth.language_tokens(c["vocab_size"])
+    ctx = _multilingual_ctx(c, w, compute, tok)
+    orc = WhisperOracle(Config(**c), w)
+    f = filters.mel_filters(80)
+    for seed, kind in ((0, "gauss"), (1, "uniform"), (2, "bursts")):
+        pcm = synth.synth_pcm(kind, seed)
+        ctx.pcm_to_mel(pcm)
+        ctx.encoder_forward(None, 1, want_output=False)
+        got_tok, got_p = ctx.detect_language(langs)
+        xa = orc.encoder_forward(torch.from_numpy(mel_c.pcm_to_mel(pcm, f)[None, :, :3000]))
+        exp_tok, exp_p = detect_language(orc, tok["sot"], langs, xa)
+        assert abs(got_p.sum() - 1.0) < 1e-5
+        tol = 1e-5 if compute == "f32" else 1e-2  # bf16 encoder: <= 1e-2 relative (SURVEY §8 d)
+        assert np.abs(got_p - exp_p).max() < tol, np.abs(got_p - exp_p).max()
+        top2 = np.sort(exp_p)[-2:]
+        if top2[1] - top2[0] > 4 * tol:
+            assert got_tok == exp_tok
+        assert got_tok in langs
+    # ties go to the EARLIER language (stable descending sort): all-equal logits -> <|en|>
+    flat = dict(w)
+    e = flat["model.decoder.embed_tokens.weight"].clone()
+    e[langs[0]: langs[-1] + 1] = 0.0
+    flat["model.decoder.embed_tokens.weight"] = e
+    ctx2 = _multilingual_ctx(c, flat, compute, tok)
+    ctx2.pcm_to_mel(synth.synth_pcm("gauss", 0))
+    ctx2.encoder_forward(None, 1, want_output=False)
+    t, p = ctx2.detect_language(langs)
+    assert t == langs[0] and np.allclose(p, 1.0 / 99, atol=1e-7)
+    ctx.close()
+    ctx2.close()
+
+
+def test_detect_language_argument_checks(lib):
+    c = synth.model_config("test-micro")
+    ctx = _multilingual_ctx(c, synth.synth_weights(c, seed=1), "f32", synth.special_tokens(c["vocab_size"]))
+    with pytest.raises(ffi.Nb200Error) as e:  # no audio features resident yet
+        ctx.detect_language([50258, 50259])
+    assert e.value.status == 4
+    ctx.transcode_batch(synth.synth_pcm("gauss", 0)[None], want_output=False)
+    with pytest.raises(ffi.Nb200Error) as e:
+        ctx.detect_language([])
+    assert e.value.status == 1
+    with pytest.raises(ffi.Nb200Error) as e:
+        ctx.detect_language([c["vocab_size"]])
+    assert e.value.status == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("task", ["transcribe", "translate"])
+def test_multilingual_transcribe_detects_then_decodes(lib, task):
+    """multilingual::Definition (LanguageState::Detect): a planted decoder that names <|fr|> at position 0 and then follows the same
+    plan as the monolingual test; host loop + device detect/decode against the Python restatement over the CPU oracle."""
+    from oracle.whisper_oracle import SpecialTokens, detect_language
+
+    c = synth.model_config("tiny")
+    tok = synth.special_tokens(c["vocab_size"], task=task, lang=None)
+    langs = synth.language_tokens(c["vocab_size"])
+    fr = langs[6]
+    ts = lambda s: tok["no_timestamps"] + 1 + int(round(s / 0.02))
+    plan = {0: fr, 1: 8, 2: ts(0.0), 3: 100, 4: 200, 5: ts(2.0), 6: ts(2.02), 7: 300, 8: tok["eot"]}
+    w = synth.plant_decoder_plan(synth.synth_weights(c, seed=1, embed_scale=1.0), c, plan)
+    d = whisper.MultilingualDefinition.new(whisper.MultilingualModelType.Tiny, whisper.SelectedDevice.Cuda(0), whisper.Task(task))
+    d.set_responsiveness(10_000)
+    model = d.blocking_try_to_model(w, compute="f32", vocab=VOCAB)
+    assert model.language() == (None, 0)
+    orc = WhisperOracle(Config(**c), w)
+    f = filters.mel_filters(80)
+    state = {}
+
+    def encode(sl):
+        state["xa"] = orc.encoder_forward(torch.from_numpy(mel_c.pcm_to_mel(np.asarray(sl, np.float32), f)[None, :, :3000]))
+
+    ref = None
+
+    def decode(t):
+        assert t == 0.0
+        st = SpecialTokens(tok["sot"], tok["eot"], tok["task"], ref.language_token, tok["no_speech"], tok["no_timestamps"], tok["ts_zero"], tok["ts_one"])
+        dr = GreedyDecoder(orc, st).decode(state["xa"])
+        assert min(dr.margins) > 0.5
+        return dr.tokens, dr.avg_logprob, dr.no_speech_prob
+
+    detok = lambda toks: b"".join(VOCAB.get(t, b"") for t in toks if t < tok["eot"]).decode()
+    ref = HostModelOracle(encode, decode, orc.reset_kv_cache, tok["no_timestamps"], tok["eot"], detok,
+                          detect_language=lambda: detect_language(orc, tok["sot"], langs, state["xa"])[0])
+    pcm = synth.synth_pcm("gauss", 3, 480_000)
+    for lo, hi, final, lang_after in ((0, 160_000, False, fr), (160_000, 480_000, True, None)):
+        got = model.transcribe(pcm[lo:hi].copy(), final)
+        exp = ref.transcribe(pcm[lo:hi].tolist(), final)
+        assert got[1] == exp[1] and got[0] == exp[0] and len(exp[1]) >= 1
+        assert model.language()[0] == lang_after == ref.language_token
+    assert model.language()[1] == 1  # one detection for the whole transcription (model.rs:170)
+    model.close()
+
+
+def test_multi_as_mono_pins_the_language(lib):
+    """monolingual::ModelType::MultiAsMono { model, lang }: multilingual weights, ConstLang(<|de|>) in the prompt, no detection."""
+    c = synth.model_config("tiny")
+    mono = whisper.ModelType.MultiAsMono(whisper.MultilingualModelType.Tiny, whisper.Language.from_code("de"))
+    d = whisper.Definition.new(mono, whisper.SelectedDevice.Cuda(0))
+    model = d.blocking_try_to_model(synth.synth_weights(c, seed=1), compute="f32")
+    de = synth.language_tokens(c["vocab_size"])[2]
+    assert model.language() == (de, 0)
+    r = model.ctx
+    r.transcode_batch(synth.synth_pcm("gauss", 0)[None], want_output=False)
+    assert r.decode(1, 0.0, max_new_tokens=2)[0]["tokens"][:3] == [50258, de, 50359]
+    model.close()
+    r.close()
+
+
+# ---- checkpoint files (SURVEY §8 f-1) --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("compute,store", [("f32", "f32"), ("bf16", "f32"), ("f32", "f16")])
+def test_model_from_files_equals_model_from_tensors(lib, tmp_path, compute, store):
+    """config.json + tokenizer.json + model.safetensors -> nb200_model_from_files: same segments as the in-memory load, and the
+    text is the tokenizer's decode of the emitted tokens (`self.tokenizer.decode(&tokens[1..len-1], true)`, model.rs:147)."""
+    c, st, w, plan = planted("tiny.en")
+    if store == "f16":
+        w = {k: v.half().float() for k, v in w.items()}  # what an F16 file holds, so both loads see identical values
+    files = synth.write_checkpoint(str(tmp_path / "ckpt"), c, {k: (v.half() if store == "f16" else v) for k, v in w.items()}, suppress_tokens=[5, 6])
+    d = whisper.Definition.new(whisper.ModelType.TinyEn, whisper.SelectedDevice.Cuda(0))
+    d.set_responsiveness(10_000)
+    a = d.blocking_try_to_model_from_files(*files, compute=compute)
+    b = d.blocking_try_to_model(w, compute=compute, suppress_tokens=[5, 6])
+    tk = ffi.Tokenizer(files[1])
+    pcm = synth.synth_pcm("gauss", 3, 480_000)
+    for lo, hi, final in ((0, 160_000, False), (160_000, 480_000, True)):
+        ga = a.transcribe(pcm[lo:hi].copy(), final)
+        gb = b.transcribe(pcm[lo:hi].copy(), final)
+        assert ga[1] == gb[1] and len(ga[1]) >= 1
+        assert ga[0] == "".join(tk.decode(s[1:-1], True) for s in ga[1])
+    assert a.ctx.query("vocab") == c["vocab_size"] and a.language() == (st.lang, 0)
+    a.close()
+    b.close()
+    b.ctx.close()
+
+
+def test_model_from_files_multilingual_and_errors(lib, tmp_path):
+    c = synth.model_config("tiny")
+    w = synth.synth_weights(c, seed=1)
+    files = synth.write_checkpoint(str(tmp_path / "m"), c, w)
+    d = whisper.MultilingualDefinition.new(whisper.MultilingualModelType.Tiny, whisper.SelectedDevice.Cuda(0), whisper.Task.Translate)
+    m = d.blocking_try_to_model_from_files(*files, compute="f32")
+    assert m.language() == (None, 0)
+    m.transcribe(synth.synth_pcm("gauss", 0, 32_000), False)
+    lang, n = m.language()
+    assert n == 1 and lang in synth.language_tokens(c["vocab_size"])
+    m.close()
+    # a checkpoint with a tensor missing: candle's "cannot find tensor" -> NOT_LOADED at finalize, nothing leaks through
+    w2 = {k: v for k, v in w.items() if k != "model.encoder.layers.1.fc1.bias"}
+    bad = synth.write_checkpoint(str(tmp_path / "bad"), c, w2)
+    with pytest.raises(ffi.Nb200Error) as e:
+        d.blocking_try_to_model_from_files(*bad, compute="f32")
+    assert "model.encoder.layers.1.fc1.bias" in str(e.value)
+    # 64 mel bins: whisper::Error::MelBins before any device work
+    c64 = dict(c, num_mel_bins=64)
+    odd = synth.write_checkpoint(str(tmp_path / "odd"), c64, {})
+    with pytest.raises(ffi.Nb200Error) as e:
+        d.blocking_try_to_model_from_files(*odd, compute="f32")
+    assert e.value.status == 5 and "Unexpected number of mel bins" in str(e.value)

@@ -145,3 +145,72 @@ def test_public_api_mirror():
     assert whisper.ModelType.TinyEn.rev() == "refs/pr/15" and whisper.ModelType.DistilLargeEnV3.vocab_version() == "V2"
     with pytest.raises(whisper.WhisperError):
         whisper.Definition.new(whisper.ModelType.TinyEn, whisper.SelectedDevice.Cpu()).blocking_try_to_model({})
+
+
+# ---- LanguageState (model.rs:392-440; multilingual.rs:319-322) --------------------------------------------------------
+MTOK = synth.special_tokens(51865, lang=None)
+LANGS = synth.language_tokens(51865)
+
+
+def _multilingual_pair(script, languages):
+    m = whisper.Model(None, MTOK, 400_000)
+    m.set_language_detection(LANGS)
+    for s in script:
+        m.script_push(*s)
+    for lang in languages:
+        m.script_push_language(lang)
+    it, lit = iter(script), iter(languages)
+    orc = HostModelOracle(lambda sl: None, lambda t: next(it), lambda: None, MTOK["no_timestamps"], MTOK["eot"], detect_language=lambda: next(lit))
+    return m, orc
+
+
+def test_language_is_detected_once_per_transcription_and_cleared_on_final_chunk():
+    nts, eot = MTOK["no_timestamps"], MTOK["eot"]
+    ts = lambda sec: nts + 1 + int(round(sec / 0.02))
+    whole = ([MTOK["sot"], LANGS[2], MTOK["task"], ts(0), 1, 2, eot], -0.2, 0.01)
+    m, orc = _multilingual_pair([whole] * 4, [LANGS[2], LANGS[6]])
+    assert m.language() == (None, 0)
+    for k, (n, final, want_lang, want_detects) in enumerate([(480_000, False, LANGS[2], 1), (480_000, False, LANGS[2], 1),
+                                                              (480_000, True, None, 1), (480_000, False, LANGS[6], 2)]):
+        got = m.transcribe(np.zeros(n, np.float32), final)
+        ref = orc.transcribe([0.0] * n, final)
+        assert got[1] == ref[1]
+        assert m.language() == (want_lang, want_detects), k
+        assert orc.language_token == want_lang
+    m.close()
+
+
+def test_const_lang_models_never_detect():
+    m = whisper.Model(None, TOK, 400_000)
+    m.script_push(PROMPT + [TS(0), 1, EOT], -0.2, 0.01)
+    m.transcribe(np.zeros(480_000, np.float32), True)
+    assert m.language() == (LANG, 0)  # LanguageState::ConstLang: clear() and set_language_token() are no-ops
+    m.close()
+
+
+def test_detection_failure_is_reported_not_swallowed():
+    m = whisper.Model(None, MTOK, 400_000)
+    m.set_language_detection(LANGS)
+    m.script_push([MTOK["sot"], LANGS[0], MTOK["task"], MTOK["no_timestamps"] + 1, 1, MTOK["eot"]], -0.2, 0.01)
+    with pytest.raises(Exception) as e:  # the scripted backend has no language queued
+        m.transcribe(np.zeros(16_000, np.float32), False)
+    assert "ran out of detected languages" in str(e.value)
+    m.script_push_language(12345)        # not one of the language tokens
+    with pytest.raises(Exception) as e:
+        m.transcribe(np.zeros(0, np.float32), False)
+    assert "not one of the language tokens" in str(e.value)
+    m.close()
+
+
+def test_public_api_mirror_of_multilingual_definitions():
+    d = whisper.MultilingualDefinition.new(whisper.MultilingualModelType.LargeV3, whisper.SelectedDevice.Cuda(0), whisper.Task.Translate)
+    assert d.detect and d.task is whisper.Task.Translate and d.model.id() == "openai/whisper-large-v3" and d.model.vocab_version() == "V2"
+    assert whisper.MultilingualModelType.default() is whisper.MultilingualModelType.Medium
+    assert whisper.MultilingualModelType.Base.rev() == "refs/pr/22" and whisper.MultilingualModelType.QuantizedTiny.quantized_ext() == "tiny"
+    mono = whisper.ModelType.MultiAsMono(whisper.MultilingualModelType.Small, whisper.Language.from_code("de"))
+    dd = whisper.Definition.new(mono, whisper.SelectedDevice.Cuda(1))
+    assert not dd.detect and dd.model.language().token() == "<|de|>" and dd.model.id() == "openai/whisper-small"
+    assert [l.token() for l in whisper.Language.iter()][:3] == ["<|en|>", "<|zh|>", "<|de|>"] and len(whisper.Language.iter()) == 99
+    assert whisper.ModelType.TinyEn.language() == whisper.Language.English
+    with pytest.raises(whisper.Respnsivness):
+        d.set_responsiveness(500)
