@@ -2,41 +2,40 @@
 // Replaces candle's materialised [B, h, 1500, 1500] f32 score tensor + softmax_last_dim + second batched matmul
 // (reached from /root/reference/src/models/whisper/model.rs:455-464; SURVEY §2b "attention").
 //
-// One CTA = one 128-row query tile of one (window, head); two CTAs are resident per SM so one CTA's softmax
-// overlaps the other's tensor-core work.  q and k arrive pre-scaled by head_dim^-0.25 each (QKV GEMM epilogue).
-//   warp 0      TMA producer: Q tile once, then K_j / V_j tiles (128 keys x 64, SWIZZLE_128B) double-buffered
-//   warp 1      MMA issuer (one thread):  S = Q . K_j^T  -> TMEM cols [0,128)   (UMMA 128x128x16, K-major A and B)
-//                                         O += P_j . V_j -> TMEM cols [128,192) (UMMA 128x64x16, V is the MN-major B)
-//                                         L += P_j . 1   -> TMEM cols [192,208) (UMMA 128x16x16 against a block of ones):
-//                                         the softmax row sums come off the tensor core, not a serial FADD chain
-//   warps 2-5   softmax: thread = query row (TMEM lane).  tcgen05.ld the S row, running max in fp32, then
-//               ex2.approx.ftz.bf16x2: two exponentials per MUFU op whose result IS the bf16 P operand; P -> shared memory
-//               in the UMMA K-major SWIZZLE_128B layout; when a row maximum grows the O and L accumulator rows are
-//               rescaled in TMEM (tcgen05.ld / st); final O / l -> bf16 -> global.
-// Measured dead ends (profiles/r1c_attention_notes.md): moving a fraction of the fp32 exponentials to an FMA-pipe
-// polynomial made the kernel slower (it trades MUFU cycles for issue slots about 1:1).
-// S(j+1) is issued as soon as the softmax warps have pulled S(j) into registers, so QK^T overlaps the exp phase.
+// Persistent kernel: 2 CTAs per SM stay resident and walk the (window, head, 128-row query tile) items round-robin.  q and k
+// arrive pre-scaled by head_dim^-0.25 each (QKV GEMM epilogue).  Per CTA:
+//   warp 0      TMA producer: Q tile of the item (double-buffered across items), then K_j / V_j tiles (64 keys x 64, SWIZZLE_128B)
+//               through a 4-stage ring
+//   warp 1      MMA issuer (one thread):  S_j = Q . K_j^T -> one of three 64-column score buffers in TMEM (UMMA 128x64x16, SS)
+//                                         O += P_j . V_j  -> TMEM columns [192, 256)  (UMMA 128x64x16, A = P_j read from TMEM,
+//                                                            V is the MN-major B operand)
+//   warps 2-5   softmax: thread = query row (TMEM lane).  tcgen05.ld the S row, online softmax in fp32 (ex2.approx), and the bf16
+//               probabilities go straight back into the TMEM columns the scores came from (tcgen05.st): P never touches shared
+//               memory.  The running maximum only moves when a row outgrows it by 2^8 (lazy rescale), so the O accumulator is
+//               rarely touched; final O / l -> bf16 -> global.
+// Nothing in the softmax loop waits for P.V: the scores of the next two tiles are already in the other S buffers, and the tensor
+// core computes the first scores of the next item while the softmax warps write this item's output.
+//
+// How it got here, with the measurements (profiles/r1d_attention_notes.md): the bound for head_dim 64 on B200 is the XU pipe
+// (16 ex2 / clk / SM: 1024 clk per 128 x 128 tile, measured by scripts/probes/mufu_probe.cu), not the tensor core (512 clk); the
+// first kernel (one P buffer in shared memory, one CTA per item) sat at ~1840 clk per tile because (a) ptxas sinks the exponentials
+// of tile j+1 below the wait for P(j).V(j) whatever the source order, (b) "some row's maximum grew" is true for most tiles when a
+// warp owns 32 rows, so the O rescale and its wait ran almost every tile, and (c) every CTA paid ~5 us of launch / TMEM alloc /
+// pipeline fill / write-out.  (a) is removed by aliasing P onto S with three S buffers, (b) by the lazy rescale, (c) by persistence.
 #include "common.cuh"
 #include "ptx.cuh"
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace {
 
-constexpr int AT_BM = 128, AT_BN = 128;
+constexpr int AT_BM = 128;
 constexpr int AT_THREADS = 192;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB: a [128 x 64] bf16 tile
-// shared memory map (base must be 1024-aligned)
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + TILE_BYTES;       // 2 stages
-constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;   // 2 stages
-constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;   // 2 sub-tiles of [128 x 64]
-constexpr int OFF_ONES = OFF_P + 2 * TILE_BYTES;  // 768 B of bf16 1.0 (the B operand of the row-sum MMA reads 512 B)
-constexpr int OFF_BAR = OFF_ONES + 768;
-constexpr int AT_SMEM = OFF_BAR + 128;  // 2 x (AT_SMEM + 1 KB system reserve) must stay <= 228 KB: two CTAs per SM
-static_assert(2 * (AT_SMEM + 1024) <= 233472, "two attention CTAs must fit one SM");
-constexpr int AT_TMEM_COLS = 256;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_LOG2 = 8.0f;  // lazy-rescale threshold in log2 units
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -44,291 +43,339 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-struct SoftmaxCtx {
-    uint32_t tS, tO, lane_off, s_full, s_empty, p_full, o_done;
-    uint8_t *p_row;
-    int rx, lane;
-};
-
-// One K/V tile of the online softmax for this thread's query row.  MASK is a template parameter so the tail masking
-// (keys >= T exist only in the last tile) is not if-converted into per-element selects on every tile.
-// two exponentials per MUFU op; the packed bf16 result is the P operand as it goes to shared memory
-__device__ __forceinline__ uint32_t ex2_bf16x2(float x0, float x1) {
-    uint32_t packed, y;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(x1), "f"(x0));  // low half <- x0
-    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(packed));
-    return y;
+// Empty asm that consumes 16 registers: everything they depend on is computed before the next asm volatile as far as nvcc is
+// concerned (ptxas may still sink it).  Only the timing build uses it, to keep the clock64 brackets honest.
+__device__ __forceinline__ void pin16(const uint32_t *r) {
+    asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                 "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
 }
 
-// One K/V tile of the online softmax for this thread's query row.  MASK is a template parameter: keys >= T exist only
-// in the last tile.
-template <bool MASK, bool BF16EXP, bool ONES>
-__device__ __forceinline__ void softmax_tile(const SoftmaxCtx &c, int j, int T, float &m, float &l) {
-    ptx::mbar_wait(c.s_full, (uint32_t)(j & 1));
+#ifdef NB200_ATTN_TIMING
+#define AT_CLK(x) x = clock64()
+#else
+#define AT_CLK(x)
+#endif
+template <bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t tSj, uint32_t tO, uint32_t s_full, uint32_t s_par, uint32_t p_full, uint32_t o_done, uint32_t o_par_prev,
+                                              int lane, bool first, int valid, float &m, float &l, long long *tm = nullptr) {
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+    AT_CLK(c0);
+    ptx::mbar_wait(s_full, s_par);
     ptx::tc_fence_after();
-    uint32_t sv[128];
-    ptx::tmem_ld_32x32b_x32(c.tS + c.lane_off + 0, sv);
-    ptx::tmem_ld_32x32b_x32(c.tS + c.lane_off + 32, sv + 32);
-    ptx::tmem_ld_32x32b_x32(c.tS + c.lane_off + 64, sv + 64);
-    ptx::tmem_ld_32x32b_x32(c.tS + c.lane_off + 96, sv + 96);
+    AT_CLK(c1);
+    uint32_t sv[64];
+    ptx::tmem_ld_32x32b_x32(tSj, sv);
+    ptx::tmem_ld_32x32b_x32(tSj + 32, sv + 32);
     ptx::tmem_ld_wait();
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (c.lane == 0) ptx::mbar_arrive(c.s_empty);
-    float mx = -INFINITY;
+    AT_CLK(c2);
     if (MASK) {
-        const int valid = T - j * AT_BN;  // >= 1
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-            float s = (i < valid) ? __uint_as_float(sv[i]) : -INFINITY;
-            sv[i] = __float_as_uint(s);
-            mx = fmaxf(mx, s);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 64; ++i)
+            if (i >= valid) sv[i] = __float_as_uint(-INFINITY);
     }
-    const float m_new = fmaxf(m, mx);
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])));
+    }
+    const float m_cand = fmaxf(fmaxf(m, fmaxf(mx0, mx1)), fmaxf(mx2, mx3));
+    // lazy rescale: the reference point of the exponentials only moves when some row of this warp outgrew it by more than 2^8
+    // (RESCALE_LOG2); until then p = 2^(s - m_stale) <= 256, exact enough in bf16 / fp32, and l, O stay consistent with m_stale
+    const bool moved = __any_sync(0xffffffffu, (m_cand - m) * LOG2E > RESCALE_LOG2);
+    const float m_new = moved ? m_cand : m;
     const float mb = m_new * LOG2E;
-    uint32_t pk[64];
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-        const float x0 = fmaf(__uint_as_float(sv[2 * i]), LOG2E, -mb), x1 = fmaf(__uint_as_float(sv[2 * i + 1]), LOG2E, -mb);
-        if (BF16EXP) {
-            pk[i] = ex2_bf16x2(x0, x1);
-            if (!ONES) {
-                rs0 += __uint_as_float(pk[i] << 16);
-                rs1 += __uint_as_float(pk[i] & 0xffff0000u);
-            }
-        } else {
-            const float p0 = ex2(x0), p1 = ex2(x1);
-            if (!ONES) { rs0 += p0; rs1 += p1; }
-            __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-            pk[i] = *(uint32_t *)&t;
-        }
+    for (int i = 0; i < 32; ++i) {
+        const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), LOG2E, -mb)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), LOG2E, -mb));
+        rs0 += p0;
+        rs1 += p1;
+        __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+        sv[i] = *(uint32_t *)&t;
     }
-    if (!ONES) l = l * ex2((m - m_new) * LOG2E) + (rs0 + rs1);
-    if (j > 0) {
-        ptx::mbar_wait(c.o_done, (uint32_t)((j - 1) & 1));  // P.V(j-1) retired: P buffer free, O / L readable
+    const float alpha = ex2((m - m_new) * LOG2E);
+    l = l * alpha + (rs0 + rs1);
+#ifdef NB200_ATTN_TIMING
+    pin16(sv); pin16(sv + 16);
+#endif
+    AT_CLK(c3);
+    ptx::tmem_st_32x32b_x32(tSj, sv);  // P(j): 64 bf16 = 32 packed columns, over the first half of S(j)
+    AT_CLK(c4);
+    if (!first && moved) {
+        ptx::mbar_wait(o_done, o_par_prev);  // only a rescale has to see P(j-1).V(j-1) retired
         ptx::tc_fence_after();
-    }
-    // P row -> smem, K-major SWIZZLE_128B: 16-byte chunk c of row r lives at chunk (c ^ (r & 7))
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            uint4 v = make_uint4(pk[t * 32 + cc * 4], pk[t * 32 + cc * 4 + 1], pk[t * 32 + cc * 4 + 2], pk[t * 32 + cc * 4 + 3]);
-            *(uint4 *)(c.p_row + t * TILE_BYTES + ((cc ^ c.rx) << 4)) = v;
-        }
-    if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
-        // rescale this warp's 32 rows of O (64 columns) and L (16 columns; the chunk's other 16 are unused TMEM) by
-        // alpha = 2^(m_old - m_new) (1 for rows whose maximum did not move)
-        const float alpha = ex2((m - m_new) * LOG2E);
-#pragma unroll
-        for (int hh = 0; hh < (ONES ? 3 : 2); ++hh) {
+        for (int hh = 0; hh < 2; ++hh) {
             uint32_t ov[32];
-            ptx::tmem_ld_32x32b_x32(c.tO + c.lane_off + hh * 32, ov);
+            ptx::tmem_ld_32x32b_x32(tO + hh * 32, ov);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            ptx::tmem_st_32x32b_x32(c.tO + c.lane_off + hh * 32, ov);
+            ptx::tmem_st_32x32b_x32(tO + hh * 32, ov);
         }
-        ptx::tmem_st_wait();
     }
+#ifdef NB200_ATTN_TIMING
+    if (tm && !first && moved) tm[6] += 1;
+#endif
+    AT_CLK(c5);
     m = m_new;
-    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    ptx::tmem_st_wait();
     ptx::tc_fence_before();
     __syncwarp();
-    if (c.lane == 0) ptx::mbar_arrive(c.p_full);
+    if (lane == 0) ptx::mbar_arrive(p_full);
+#ifdef NB200_ATTN_TIMING
+    if (tm) {
+        const long long c6 = clock64();
+        tm[0] += c1 - c0; tm[1] += c2 - c1; tm[2] += c3 - c2; tm[3] += c4 - c3; tm[4] += c5 - c4; tm[5] += c6 - c5; tm[7] += 1;
+    }
+#endif
 }
 
-template <bool BF16EXP, bool ONES>
+struct AtCfg {
+    static constexpr int BN = 64;
+    static constexpr int KV_BYTES = BN * 64 * 2;  // 8 KB
+    static constexpr int ST = 4;                  // K / V stages
+    static constexpr int NS = 3;                  // S buffers in TMEM
+    static constexpr int OFF_Q = 0;               // 2 x 16 KB
+    static constexpr int OFF_K = 2 * TILE_BYTES;
+    static constexpr int OFF_V = OFF_K + ST * KV_BYTES;
+    static constexpr int OFF_BAR = OFF_V + ST * KV_BYTES;
+    static constexpr int SMEM = OFF_BAR + 256;
+    static constexpr int TMEM_COLS = 256;  // S0 | S1 | S2 | O
+    // barrier block (8 B each): q_full[2] q_empty[2] k_full[ST] k_empty[ST] v_full[ST] v_empty[ST] s_full[NS] p_full[NS] o_done, then the TMEM slot
+    static constexpr int B_QF = 0, B_QE = 16, B_KF = 32, B_KE = B_KF + 8 * ST, B_VF = B_KE + 8 * ST, B_VE = B_VF + 8 * ST, B_SF = B_VE + 8 * ST,
+                         B_PF = B_SF + 8 * NS, B_OD = B_PF + 8 * NS, B_SLOT = B_OD + 8;
+    static_assert(B_SLOT + 4 <= 256, "barrier block");
+};
+static_assert(2 * (AtCfg::SMEM + 1024) <= 233472, "two attention CTAs must fit one SM");
+
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16 *__restrict__ out, int T, int d) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, bf16 *__restrict__ out, int T, int d, int n_heads, int n_items,
+                unsigned long long *dbg) {
+    using L = AtCfg;
+    constexpr int BN = L::BN, ST = L::ST, NS = L::NS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = ptx::smem_u32(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int q0 = qt * AT_BM;
-    const int nkv = (T + AT_BN - 1) / AT_BN;
+    const int nq = (T + AT_BM - 1) / AT_BM;
+    const int nkv = (T + BN - 1) / BN;
+    const uint32_t sQ = sbase + L::OFF_Q, sK = sbase + L::OFF_K, sV = sbase + L::OFF_V;
+    const uint32_t bar = sbase + L::OFF_BAR;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + L::OFF_BAR + L::B_SLOT);
+    // items this CTA owns: blockIdx.x, blockIdx.x + gridDim.x, ...   item -> (query tile fastest, then head, then window)
+    const int my_items = n_items > (int)blockIdx.x ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    const uint32_t sQ = sbase + OFF_Q, sK = sbase + OFF_K, sV = sbase + OFF_V, sP = sbase + OFF_P;
-    const uint32_t bar = sbase + OFF_BAR;
-    // K and V have separate 2-deep rings: the K stage is free as soon as S = Q.K^T has been computed, the V stage only after
-    // P.V retires, so K(j+1) can be in flight two tiles ahead and S(j+1) never waits behind P.V(j-1) -> TMA -> K(j+1)
-    const uint32_t q_full = bar, k_full0 = bar + 8, k_empty0 = bar + 24, v_full0 = bar + 40, v_empty0 = bar + 56, s_full = bar + 72,
-                   s_empty = bar + 80, p_full = bar + 88, o_done = bar + 96, tmem_slot = bar + 104;
-    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + OFF_BAR + 104);
-
-    if (threadIdx.x == 0 && (sbase & 1023u)) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base
-    ((uint32_t *)(smem_raw + OFF_ONES))[threadIdx.x] = 0x3F803F80u;  // 192 threads x 4 B = 768 B of bf16 1.0
-    ptx::fence_proxy_async();
-    if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmQKV);
+    if (threadIdx.x == 0 && (sbase & 1023u)) __trap();
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmKV);
+    }
     if (warp == 1 && lane == 0) {
-        ptx::mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) {
-            ptx::mbar_init(k_full0 + 8 * s, 1);
-            ptx::mbar_init(k_empty0 + 8 * s, 1);
-            ptx::mbar_init(v_full0 + 8 * s, 1);
-            ptx::mbar_init(v_empty0 + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_QF + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_QE + 8 * s, 1);
         }
-        ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(s_empty, 4);
-        ptx::mbar_init(p_full, 4);
-        ptx::mbar_init(o_done, 1);
+        for (int s = 0; s < ST; ++s) {
+            ptx::mbar_init(bar + L::B_KF + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_KE + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_VF + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_VE + 8 * s, 1);
+        }
+        for (int s = 0; s < NS; ++s) {
+            ptx::mbar_init(bar + L::B_SF + 8 * s, 1);
+            ptx::mbar_init(bar + L::B_PF + 8 * s, 4);
+        }
+        ptx::mbar_init(bar + L::B_OD, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+        ptx::tmem_alloc(bar + L::B_SLOT, L::TMEM_COLS);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t tS = tmem_base, tO = tmem_base + 128, tL = tmem_base + 192;
+    const uint32_t tO = tmem_base + NS * 64;
 
     if (warp == 0) {
         if (lane == 0) {
-            ptx::mbar_expect_tx(q_full, TILE_BYTES);
-            ptx::tma_load_3d(sQ, &tmQKV, q_full, h * HEAD_DIM, q0, b);
-            // K runs ahead of V: K(j) is requested as soon as S(j-2) has been computed
-            for (int j = 0; j < nkv + 1; ++j) {
-                if (j < nkv) {
-                    const int s = j & 1;
-                    if (j >= 2) ptx::mbar_wait(k_empty0 + 8 * s, (uint32_t)(((j >> 1) & 1) ^ 1));
-                    ptx::mbar_expect_tx(k_full0 + 8 * s, TILE_BYTES);
-                    ptx::tma_load_3d(sK + s * TILE_BYTES, &tmQKV, k_full0 + 8 * s, d + h * HEAD_DIM, j * AT_BN, b);
-                }
-                if (j >= 1) {
-                    const int jv = j - 1, s = jv & 1;
-                    if (jv >= 2) ptx::mbar_wait(v_empty0 + 8 * s, (uint32_t)(((jv >> 1) & 1) ^ 1));
-                    ptx::mbar_expect_tx(v_full0 + 8 * s, TILE_BYTES);
-                    ptx::tma_load_3d(sV + s * TILE_BYTES, &tmQKV, v_full0 + 8 * s, 2 * d + h * HEAD_DIM, jv * AT_BN, b);
+            int g = 0;  // running K/V tile count of this CTA
+            for (int it = 0; it < my_items; ++it) {
+                const int item = (int)blockIdx.x + it * (int)gridDim.x;
+                const int qt = item % nq, hh = (item / nq) % n_heads, b = item / (nq * n_heads);
+                const int qb = it & 1;
+                if (it >= 2) ptx::mbar_wait(bar + L::B_QE + 8 * qb, (uint32_t)(((it >> 1) & 1) ^ 1));  // every S = Q.K^T of item it-2 has retired
+                ptx::mbar_expect_tx(bar + L::B_QF + 8 * qb, TILE_BYTES);
+                ptx::tma_load_3d(sQ + qb * TILE_BYTES, &tmQ, bar + L::B_QF + 8 * qb, hh * HEAD_DIM, qt * AT_BM, b);
+                for (int j = 0; j < nkv; ++j, ++g) {
+                    const int s = g % ST;
+                    const uint32_t ph = (uint32_t)(((g / ST) & 1) ^ 1);
+                    if (g >= ST) ptx::mbar_wait(bar + L::B_KE + 8 * s, ph);
+                    ptx::mbar_expect_tx(bar + L::B_KF + 8 * s, L::KV_BYTES);
+                    ptx::tma_load_3d(sK + s * L::KV_BYTES, &tmKV, bar + L::B_KF + 8 * s, d + hh * HEAD_DIM, j * BN, b);
+                    if (g >= ST) ptx::mbar_wait(bar + L::B_VE + 8 * s, ph);
+                    ptx::mbar_expect_tx(bar + L::B_VF + 8 * s, L::KV_BYTES);
+                    ptx::tma_load_3d(sV + s * L::KV_BYTES, &tmKV, bar + L::B_VF + 8 * s, 2 * d + hh * HEAD_DIM, j * BN, b);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_BM, AT_BN, 0, 0);
+            constexpr uint32_t idesc_s = ptx::make_idesc_bf16(AT_BM, BN, 0, 0);
             constexpr uint32_t idesc_o = ptx::make_idesc_bf16(AT_BM, HEAD_DIM, 0, 1);  // B (= V) is MN-major
-            constexpr uint32_t idesc_l = ptx::make_idesc_bf16(AT_BM, 16, 0, 0);
-            const uint64_t d_ones = ptx::make_nosw_desc(sbase + OFF_ONES, 128, 256);  // 16 (N) x 16 (K) block of ones
-            auto issue_s = [&](int j) {
-                const uint32_t kb = sK + (j & 1) * TILE_BYTES;
+            const int G = my_items * nkv;
+            // S(g): g-th score tile of this CTA (item g / nkv, key tile g % nkv) -> S buffer g % NS
+            int s_it = 0, s_j = 0;  // (item, tile) of the next S to issue
+            auto issue_s = [&](int g) {
+                const int qb = s_it & 1;
+                if (s_j == 0) ptx::mbar_wait(bar + L::B_QF + 8 * qb, (uint32_t)((s_it >> 1) & 1));
+                const int s = g % ST;
+                ptx::mbar_wait(bar + L::B_KF + 8 * s, (uint32_t)((g / ST) & 1));
+                ptx::tc_fence_after();
+                const uint32_t qa = sQ + qb * TILE_BYTES, kb = sK + s * L::KV_BYTES, ts = tmem_base + (g % NS) * 64;
 #pragma unroll
                 for (int k = 0; k < HEAD_DIM / 16; ++k)
-                    ptx::mma_bf16_ss(tS, ptx::make_sw128_desc(sQ + k * 32, 16, 1024), ptx::make_sw128_desc(kb + k * 32, 16, 1024), idesc_s, k != 0);
-                ptx::mma_commit(k_empty0 + 8 * (j & 1));  // K stage reusable once S(j) is computed
-                ptx::mma_commit(s_full);
+                    ptx::mma_bf16_ss(ts, ptx::make_sw128_desc(qa + k * 32, 16, 1024), ptx::make_sw128_desc(kb + k * 32, 16, 1024), idesc_s, k != 0);
+                ptx::mma_commit(bar + L::B_KE + 8 * s);
+                ptx::mma_commit(bar + L::B_SF + 8 * (g % NS));
+                if (++s_j == nkv) {
+                    ptx::mma_commit(bar + L::B_QE + 8 * qb);  // the Q buffer may be refilled
+                    s_j = 0;
+                    ++s_it;
+                }
             };
-            ptx::mbar_wait(q_full, 0);
-            ptx::mbar_wait(k_full0, 0);
-            ptx::tc_fence_after();
-            issue_s(0);
-            for (int j = 0; j < nkv; ++j) {
-                if (j + 1 < nkv) {
-                    ptx::mbar_wait(k_full0 + 8 * ((j + 1) & 1), (uint32_t)(((j + 1) >> 1) & 1));
-                    ptx::mbar_wait(s_empty, (uint32_t)(j & 1));  // softmax has S(j) in registers
-                    ptx::tc_fence_after();
-                    issue_s(j + 1);
-                }
-                ptx::mbar_wait(v_full0 + 8 * (j & 1), (uint32_t)((j >> 1) & 1));
-                ptx::mbar_wait(p_full, (uint32_t)(j & 1));  // P(j) in smem, O rescaled
+            for (int g = 0; g < NS - 1 && g < G; ++g) issue_s(g);
+            int j = 0;
+            for (int g = 0; g < G; ++g) {
+                const int s = g % ST, sb = g % NS;
+                ptx::mbar_wait(bar + L::B_VF + 8 * s, (uint32_t)((g / ST) & 1));
+                ptx::mbar_wait(bar + L::B_PF + 8 * sb, (uint32_t)((g / NS) & 1));  // P(g) sits in the columns of S(g); O rescaled (or, j = 0, read out)
                 ptx::tc_fence_after();
-                const uint32_t vb = sV + (j & 1) * TILE_BYTES;
+                const uint32_t vb = sV + s * L::KV_BYTES, tp = tmem_base + sb * 64;
 #pragma unroll
-                for (int ks = 0; ks < AT_BN / 16; ++ks) {
-                    const uint64_t da = ptx::make_sw128_desc(sP + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
-                    const uint64_t db = ptx::make_sw128_desc(vb + ks * 2048, 1024, 1024);
-                    ptx::mma_bf16_ss(tO, da, db, idesc_o, (j | ks) != 0);
-                    if (ONES) ptx::mma_bf16_ss(tL, da, d_ones, idesc_l, (j | ks) != 0);  // row sums of the bf16 P actually used
-                }
-                ptx::mma_commit(v_empty0 + 8 * (j & 1));
-                ptx::mma_commit(o_done);
+                for (int ks = 0; ks < BN / 16; ++ks)
+                    ptx::mma_bf16_ts(tO, tp + ks * 8, ptx::make_sw128_desc(vb + ks * 2048, 1024, 1024), idesc_o, (j | ks) != 0);
+                ptx::mma_commit(bar + L::B_VE + 8 * s);
+                ptx::mma_commit(bar + L::B_OD);
+                if (++j == nkv) j = 0;
+                if (g + NS - 1 < G) issue_s(g + NS - 1);  // into the buffer S(g-1)/P(g-1) used: P(g-1).V was issued one iteration ago
             }
         }
     } else {
-        // ================= softmax warps: thread <-> query row / TMEM lane =================
         const int qd = warp & 3;
         const int r = qd * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-        float m = -INFINITY, l = 0.f;
-        uint8_t *p_row = smem_raw + OFF_P + r * 128;
-        const int rx = r & 7;
-        SoftmaxCtx sc{tS, tO, lane_off, s_full, s_empty, p_full, o_done, p_row, rx, lane};
-        for (int j = 0; j < nkv - 1; ++j) softmax_tile<false, BF16EXP, ONES>(sc, j, T, m, l);
-        softmax_tile<true, BF16EXP, ONES>(sc, nkv - 1, T, m, l);  // only the last K/V tile can hold keys >= T
-        ptx::mbar_wait(o_done, (uint32_t)((nkv - 1) & 1));
-        ptx::tc_fence_after();
-        float inv = 1.0f / l;
-        if (ONES) {
-            uint32_t lv[32];
-            ptx::tmem_ld_32x32b_x32(tL + lane_off, lv);
-            ptx::tmem_ld_wait();
-            inv = 1.0f / __uint_as_float(lv[0]);
-        }
-        const int q = q0 + r;
-        bf16 *orow = out + ((size_t)b * T + q) * d + h * HEAD_DIM;
+        int g = 0;
+        long long *tm = nullptr;
+#ifdef NB200_ATTN_TIMING
+        long long tm_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, e0 = 0, e1 = 0, e2 = 0;
+        const long long k0 = clock64();
+        tm = tm_acc;
+#endif
+        for (int it = 0; it < my_items; ++it) {
+            const int item = (int)blockIdx.x + it * (int)gridDim.x;
+            const int qt = item % nq, hh = (item / nq) % n_heads, b = item / (nq * n_heads);
+            float m = -INFINITY, l = 0.f;
+            for (int j = 0; j < nkv - 1; ++j, ++g) {
+                const int sb = g % NS;
+                softmax_tile<false>(tmem_base + lane_off + sb * 64, tO + lane_off, bar + L::B_SF + 8 * sb, (uint32_t)((g / NS) & 1), bar + L::B_PF + 8 * sb,
+                                     bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, j == 0, 64, m, l, tm);
+            }
+            {
+                const int sb = g % NS;
+                softmax_tile<true>(tmem_base + lane_off + sb * 64, tO + lane_off, bar + L::B_SF + 8 * sb, (uint32_t)((g / NS) & 1), bar + L::B_PF + 8 * sb,
+                                    bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, nkv == 1, T - (nkv - 1) * BN, m, l, tm);
+                ++g;
+            }
+            AT_CLK(e0);
+            ptx::mbar_wait(bar + L::B_OD, (uint32_t)((g - 1) & 1));  // last P.V of this item
+            ptx::tc_fence_after();
+            AT_CLK(e1);
+            const float inv = 1.0f / l;
+            const int q = qt * AT_BM + r;
+            bf16 *orow = out + ((size_t)b * T + q) * d + hh * HEAD_DIM;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            uint32_t ov[32];
-            ptx::tmem_ld_32x32b_x32(tO + lane_off + hh * 32, ov);
-            ptx::tmem_ld_wait();
-            if (q < T) {
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t ov[32];
+                ptx::tmem_ld_32x32b_x32(tO + lane_off + hf * 32, ov);
+                ptx::tmem_ld_wait();
+                if (q < T) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 v;
-                    __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
-                    __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-                    __nv_bfloat162 a2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-                    __nv_bfloat162 a3 = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-                    v.x = *(uint32_t *)&a0; v.y = *(uint32_t *)&a1; v.z = *(uint32_t *)&a2; v.w = *(uint32_t *)&a3;
-                    *(uint4 *)(orow + hh * 32 + i) = v;
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 v;
+                        __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+                        __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+                        __nv_bfloat162 a2 = __floats2bfloat162_rn(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+                        __nv_bfloat162 a3 = __floats2bfloat162_rn(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+                        v.x = *(uint32_t *)&a0; v.y = *(uint32_t *)&a1; v.z = *(uint32_t *)&a2; v.w = *(uint32_t *)&a3;
+                        *(uint4 *)(orow + hf * 32 + i) = v;
+                    }
                 }
             }
+            ptx::tc_fence_before();  // O is in registers: the next item's first P.V (ordered behind this warp's next p_full arrive) may overwrite it
+#ifdef NB200_ATTN_TIMING
+            e2 = clock64();
+            tm[8] += e1 - e0; tm[9] += e2 - e1; tm[10] += 1;
+#endif
         }
+#ifdef NB200_ATTN_TIMING
+        if (dbg && lane == 0) {
+            tm[11] = clock64() - k0;
+            for (int i = 0; i < 12; ++i) atomicAdd(dbg + i, (unsigned long long)tm[i]);
+            atomicAdd(dbg + 12, 1ull);
+        }
+#endif
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
+        ptx::tmem_dealloc(tmem_base, L::TMEM_COLS);
     }
 }
 
 }  // namespace
 
 int attn_tc_init(nb200_ctx *ctx) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg::SMEM));
     return NB200_OK;
 }
 
 // qkv: [B*T][3d] bf16 (q | k | v, heads of 64 inside each third); out: [B*T][d] bf16
 int launch_attention_tc(nb200_ctx *ctx, const bf16 *qkv, bf16 *out, int B, int T, int n_heads) {
     const int d = n_heads * HEAD_DIM;
-    CUtensorMap tm;
+    CUtensorMap tq, tkv;
     uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
-    uint32_t box[3] = {HEAD_DIM, 128, 1};
-    NB_TRY(tmap_encode_bf16(ctx, &tm, qkv, 3, dims, str, box));
+    uint32_t box_q[3] = {HEAD_DIM, AT_BM, 1}, box_kv[3] = {HEAD_DIM, AtCfg::BN, 1};
+    NB_TRY(tmap_encode_bf16(ctx, &tq, qkv, 3, dims, str, box_q));
+    NB_TRY(tmap_encode_bf16(ctx, &tkv, qkv, 3, dims, str, box_kv));
     KernelScope ks(ctx, NB200_K_ATTN);
-    dim3 grid(ceil_div(T, AT_BM), n_heads, B);
-    static int variant = -1;  // NB200_ATTN_VARIANT: bit0 = bf16x2 exp2, bit1 = row sums on the tensor core (A/B experiments)
-    if (variant < 0) {
-        const char *ev = getenv("NB200_ATTN_VARIANT");
-        variant = ev ? atoi(ev) : 0;
-    }
-    switch (variant & 3) {
-        case 0: attn_tc_kernel<false, false><<<grid, AT_THREADS, AT_SMEM, ctx->stream>>>(tm, out, T, d); break;
-        case 1: attn_tc_kernel<true, false><<<grid, AT_THREADS, AT_SMEM, ctx->stream>>>(tm, out, T, d); break;
-        case 2: attn_tc_kernel<false, true><<<grid, AT_THREADS, AT_SMEM, ctx->stream>>>(tm, out, T, d); break;
-        default: attn_tc_kernel<true, true><<<grid, AT_THREADS, AT_SMEM, ctx->stream>>>(tm, out, T, d); break;
-    }
+    const int n_items = ceil_div(T, AT_BM) * n_heads * B;   // (window, head, query tile), query tile fastest: CTAs that run together share K / V in L2
+    const int ctas = std::min(n_items, 2 * ctx->sm_count);  // persistent: two resident CTAs per SM
+    unsigned long long *dbg = nullptr;
+#ifdef NB200_ATTN_TIMING
+    static unsigned long long *dbg_buf = nullptr;
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 128);
+    cudaMemsetAsync(dbg_buf, 0, 128, ctx->stream);
+    dbg = dbg_buf;
+#endif
+    attn_tc_kernel<<<ctas, AT_THREADS, AtCfg::SMEM, ctx->stream>>>(tq, tkv, out, T, d, n_heads, n_items, dbg);
     CUDA_TRY(ctx, cudaGetLastError());
+#ifdef NB200_ATTN_TIMING  // scripts/probes: where a softmax warp's cycles go (clock64 deltas kept in registers, one atomicAdd per warp at the end)
+    {
+        unsigned long long hst[16];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hst, dbg_buf, 128, cudaMemcpyDeviceToHost);
+        const double n = (double)hst[7], w = (double)hst[12], it = (double)hst[10];
+        fprintf(stderr, "[attn timing] per warp per 64-key tile, clk: s_full wait %.0f | tmem ld %.0f | max+exp+pack %.0f | P st issue %.0f | rescale %.0f | "
+                        "st wait+arrive %.0f | rescales %.3f/tile || per item: o_done wait %.0f, O write-out %.0f || per warp: total %.0f clk, %.1f tiles, %.1f items\n",
+                hst[0] / n, hst[1] / n, hst[2] / n, hst[3] / n, hst[4] / n, hst[5] / n, hst[6] / n, hst[8] / it, hst[9] / it, hst[11] / w, n / w, it / w);
+    }
+#endif
     return NB200_OK;
 }

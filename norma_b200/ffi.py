@@ -10,7 +10,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnorma_b200.so")
+LIB_PATH = os.environ.get("NB200_LIB_PATH", os.path.join(_HERE, "libnorma_b200.so"))  # override: instrumented builds (scripts/probes)
 
 NB200_OK = 0
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH", 7: "IO_ERROR", 8: "PARSE_ERROR", 9: "NOT_FOUND"}
