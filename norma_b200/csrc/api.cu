@@ -195,6 +195,9 @@ int alloc_decoder(nb200_ctx *ctx) {
     NB_TRY(dev_alloc(ctx, 64, &ctx->d_dyn, true));
     NB_TRY(dev_alloc(ctx, B * 32 * (8 + 32), &ctx->d_sel_ws, true));
     NB_TRY(dev_alloc(ctx, (size_t)NB200_MAX_LANGS * 8 + 16, &ctx->d_lang, true));
+    NB_TRY(dev_alloc(ctx, 128 + (size_t)B * c.decoder_attention_heads * 4, &ctx->d_fused_sync, true));
+    NB_TRY(dev_alloc(ctx, (size_t)c.decoder_layers * sizeof(DecLayer), &ctx->d_dec_layers));
+    NB_TRY(dev_alloc_t(ctx, (size_t)decoder_fused_ws_floats(ctx), &ctx->d_fused_attn_ws, true));
     NB_TRY(dev_alloc_t(ctx, B * (size_t)c.decoder_attention_heads * 8 * 66, &ctx->d_attn_ws, true));
     NB_TRY(dev_alloc_t(ctx, (size_t)c.vocab_size, &ctx->suppress, true));
     return NB200_OK;
@@ -563,6 +566,8 @@ int nb200_finalize_weights(nb200_ctx *ctx) {
         }
         NB_TRY(up_vec(ctx, D + "layer_norm.weight", d, &ctx->lndec_g));
         NB_TRY(up_vec(ctx, D + "layer_norm.bias", d, &ctx->lndec_b));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dec_layers, ctx->dec.data(), ctx->dec.size() * sizeof(DecLayer), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         NB_TRY(upload_suppress(ctx));
     }
     ctx->host_tensors.clear();
@@ -914,7 +919,11 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     // Steady state: one decode step (embed .. 2 x attention .. MLP .. logits .. select) is a CUDA graph replayed with the
     // position living on the device; the host only polls the done flags every POLL steps (no per-token sync or transfer).
     std::vector<int> done(B);
-    const bool use_graph = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
+    // greedy steady state: POLL steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 falls back to the
+    // ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose sampler is a single-block kernel)
+    static const bool fused_ok = [] { const char *e = getenv("NB200_DECODE_FUSED"); return !(e && e[0] == '0'); }();
+    const bool use_fused = greedy && fused_ok && decoder_fused_supported(ctx);
+    const bool use_graph = !use_fused && !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
     cudaGraphExec_t gexec = nullptr;
     if (use_graph) {
         const int gkey = B * 2 + greedy;
@@ -933,15 +942,22 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
         } else gexec = it->second;
     }
     const int POLL = 16;
+    if (use_fused) NB_TRY(decoder_fused_prepare(ctx));
     for (int pos = plen; pos < P;) {
         CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         bool all = true;
         for (int b = 0; b < B; ++b) all &= done[b] != 0;
         if (all) break;
-        const int n = use_graph ? std::min(POLL, P - pos) : 1;
+        const int n = (use_graph || use_fused) ? std::min(POLL, P - pos) : 1;
+        if (use_fused) {  // one cooperative launch for the next n positions: the CTAs stay resident between steps
+            NB_TRY(decoder_step_fused(ctx, B, n));
+            pos += n;
+            continue;
+        }
         for (int i = 0; i < n; ++i) {
-            if (use_graph) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            if (false) {}
+            else if (use_graph) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
             else {
                 NB_TRY(decoder_step(ctx, 0, B, -1, 1));
                 NB_TRY(decoder_select(ctx, B, greedy));

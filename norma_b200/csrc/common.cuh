@@ -138,6 +138,11 @@ struct nb200_ctx {
     int *d_len = nullptr, *d_last_ts = nullptr, *d_done = nullptr, *d_nsampled = nullptr;
     double *d_sumlp = nullptr;
     float *d_nospeech = nullptr;
+    void *d_dec_layers = nullptr;  // device copy of `dec` (fused decoder step)
+    void *d_fused_sel_ws = nullptr;    // greedy-select partials of the fused step, one vocabulary chunk per CTA
+    float *d_fused_attn_ws = nullptr;  // split-K partials of the fused step's attention [max_batch][heads][64][66]
+    void *d_fused_sync = nullptr;  // monotonic grid-barrier counter (u32, own 128 B line) | attention tickets [max_batch][heads]
+    int fused_ctas = 0;            // cooperative grid of the fused decoder step (0 = not sized yet)
     void *d_lang = nullptr;      // detect_language scratch: [NB200_MAX_LANGS] u32 ids | [NB200_MAX_LANGS] f32 probs | i32 best
     void *d_sel_ws = nullptr;    // greedy select partials: [max_batch][32] float2 + [max_batch][32] SelCand
     float *d_attn_ws = nullptr;  // split-K decode attention partials [max_batch][heads][8][66]
@@ -226,6 +231,10 @@ int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int ran
 int decoder_select(nb200_ctx *ctx, int n_windows, int greedy);  // also advances the device-resident position
 int decoder_set_dyn(nb200_ctx *ctx, int pos, int max_new, float temperature, unsigned long long seed, int set_params);
 int decoder_nospeech(nb200_ctx *ctx, int n_windows);
+int decoder_step_fused(nb200_ctx *ctx, int n_windows, int n_steps);  // n_steps greedy steps in one cooperative launch (device-resident position)
+bool decoder_fused_supported(const nb200_ctx *ctx);
+int decoder_fused_prepare(nb200_ctx *ctx);
+int decoder_fused_ws_floats(const nb200_ctx *ctx);  // one greedy step, one cooperative launch (device-resident position)
 constexpr int NB200_MAX_LANGS = 1024;
 int decoder_language(nb200_ctx *ctx, int n_langs);  // softmax over logits[ids] of row 0, first-index argmax -> d_lang
 int decoder_init_state(nb200_ctx *ctx, int n_windows);

@@ -10,6 +10,9 @@
 // Replaces `Type::decoder_forward` / `decoder_final_linear` (model.rs:466-483) and `Model::decode` at t = 0
 // (model.rs:279-390) with the rules of model.rs:212-277 and the masks of monolingual.rs:386-430.
 #include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
 
 namespace {
 
@@ -299,25 +302,35 @@ decode_attn_merge_kernel(const float *__restrict__ ws, int S, float *__restrict_
     out[(size_t)b * ldo + h * HEAD_DIM + t] = o / l;
 }
 
-// ---- block reductions for the 1024-thread select kernel ----------------------------------------------------
+// ---- block reductions.  BAR = 0: the whole block (__syncthreads, blockDim.x threads); BAR > 0: the first NT threads of the block
+// through named barrier BAR (the fused step's consumer threads)
+template <int BAR, int NT>
+__device__ __forceinline__ void block_sync() {
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+template <int BAR = 0, int NT = 0>
 __device__ __forceinline__ float block_max(float v, float *red) {
+    const int nw = (NT ? NT : (int)blockDim.x) >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    __syncthreads();
+    block_sync<BAR, NT>();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
+    block_sync<BAR, NT>();
     float r = red[0];
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = fmaxf(r, red[i]);
+    for (int i = 1; i < nw; ++i) r = fmaxf(r, red[i]);
     return r;
 }
+template <int BAR = 0, int NT = 0>
 __device__ __forceinline__ float block_sum(float v, float *red) {
+    const int nw = (NT ? NT : (int)blockDim.x) >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
+    block_sync<BAR, NT>();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
+    block_sync<BAR, NT>();
     float r = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += red[i];
+    for (int i = 0; i < nw; ++i) r += red[i];
     return r;
 }
 
@@ -492,48 +505,58 @@ update_state:
 // ---- greedy (t = 0) select in three short multi-block phases (the single 1024-thread block above costs ~58 us per step
 // at V = 51 866; it remains the path for t > 0) --------------------------------------------------------------------
 constexpr int SEL_CH = 32;  // vocabulary chunks per window
-struct SelCand { float sum_ts, max_text, best_a, best_b; int idx_a, idx_b; };
+struct __align__(8) SelCand { float sum_ts, max_text, best_a, best_b; int idx_a, idx_b; };
 
-// phase A: per-chunk (max, sum exp(x - max))
+// phase A: per-chunk (max, sum exp(x - max)).  Block-uniform (b, c); BAR / NT as in block_max.
+template <int BAR = 0, int NT = 0>
+__device__ __forceinline__ void select_stats_body(const float *__restrict__ logits, int V, float2 *__restrict__ ws_a, int b, int c, int nch, float *red) {
+    const int tid = threadIdx.x, nt = NT ? NT : (int)blockDim.x;
+    const int per = (V + nch - 1) / nch, lo = c * per, hi = min(V, lo + per);
+    const float *x = logits + (size_t)b * V;
+    float lm = -INFINITY;
+#pragma unroll 1
+    for (int i = lo + tid; i < hi; i += nt) lm = fmaxf(lm, __ldcg(x + i));
+    const float mx = block_max<BAR, NT>(lm, red);
+    float ls = 0.f;
+#pragma unroll 1
+    for (int i = lo + tid; i < hi; i += nt) ls += expf(__ldcg(x + i) - mx);
+    const float sm = block_sum<BAR, NT>(ls, red);
+    if (tid == 0) ws_a[b * nch + c] = make_float2(mx, sm);
+}
 __global__ void __launch_bounds__(256)
 select_stats_kernel(const float *__restrict__ logits, int V, float2 *__restrict__ ws_a) {
     __shared__ float red[32];
-    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
-    const int per = (V + SEL_CH - 1) / SEL_CH, lo = c * per, hi = min(V, lo + per);
-    const float *x = logits + (size_t)b * V;
-    float lm = -INFINITY;
-    for (int i = lo + tid; i < hi; i += 256) lm = fmaxf(lm, x[i]);
-    const float mx = block_max(lm, red);
-    float ls = 0.f;
-    for (int i = lo + tid; i < hi; i += 256) ls += expf(x[i] - mx);
-    const float sm = block_sum(ls, red);
-    if (tid == 0) ws_a[b * SEL_CH + c] = make_float2(mx, sm);
+    select_stats_body(logits, V, ws_a, blockIdx.x, blockIdx.y, SEL_CH, red);
 }
 
 // phase B: with the global (max, sum) every chunk yields its share of sum_ts / max_text and the arg-max candidates of the
 // rule(s) that can still apply: mode 0 / 1 are known from the token state; otherwise both 2 and 3 are prepared
-__global__ void __launch_bounds__(256)
-select_cand_kernel(SelectParams sp, const float2 *__restrict__ ws_a, SelCand *__restrict__ ws_b) {
-    __shared__ float red[32];
-    __shared__ int red_i[32];
-    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
-    if (sp.done[b]) return;
+template <int BAR = 0, int NT = 0>
+__device__ __forceinline__ void select_cand_body(const SelectParams &sp, const float2 *__restrict__ ws_a, SelCand *__restrict__ ws_b, int b, int c, int nch,
+                                                 float *red, int *red_i) {
+    const int tid = threadIdx.x, nt = NT ? NT : (int)blockDim.x;
+    if (__ldcg(sp.done + b)) return;  // (state and logits change every step of a multi-step launch: read them from L2)
     const int V = sp.V, nts = (int)sp.nts;
-    float M = -INFINITY;
-    for (int k = 0; k < SEL_CH; ++k) M = fmaxf(M, ws_a[b * SEL_CH + k].x);
-    float S = 0.f;
-    for (int k = 0; k < SEL_CH; ++k) S += ws_a[b * SEL_CH + k].y * expf(ws_a[b * SEL_CH + k].x - M);
-    const int len = sp.len[b], last_ts = sp.last_ts[b];
+    // global (max, sum) from the chunk partials, folded by the whole block (one partial per thread: nch can be as large as the grid)
+    float pm = -INFINITY;
+#pragma unroll 1
+    for (int k = tid; k < nch; k += nt) pm = fmaxf(pm, __ldcg(&ws_a[b * nch + k].x));
+    const float M = block_max<BAR, NT>(pm, red);
+    float ps = 0.f;
+#pragma unroll 1
+    for (int k = tid; k < nch; k += nt) ps += __ldcg(&ws_a[b * nch + k].y) * expf(__ldcg(&ws_a[b * nch + k].x) - M);
+    const float S = block_sum<BAR, NT>(ps, red);
+    const int len = __ldcg(sp.len + b), last_ts = __ldcg(sp.last_ts + b);
     int mode_a, mode_b = -1;
     if (last_ts < 0) mode_a = 0;
     else {
-        const uint32_t l_tok = sp.tokens[(size_t)b * sp.max_pos + len - 1];
+        const uint32_t l_tok = __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 1);
         const bool has_sl = len >= 2;
-        const uint32_t sl_tok = has_sl ? sp.tokens[(size_t)b * sp.max_pos + len - 2] : 0u;
+        const uint32_t sl_tok = has_sl ? __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 2) : 0u;
         if ((int)l_tok > nts) mode_a = (has_sl && sl_tok >= sp.eot) ? 1 : 2;
         else { mode_a = 2; mode_b = 3; }
     }
-    const int per = (V + SEL_CH - 1) / SEL_CH, lo = c * per, hi = min(V, lo + per);
+    const int per = (V + nch - 1) / nch, lo = c * per, hi = min(V, lo + per);
     const float *x = sp.logits + (size_t)b * V;
     float ts = 0.f, mt = -INFINITY, ba = -INFINITY, bb = -INFINITY;
     int ia = -1, ib = -1;
@@ -545,8 +568,9 @@ select_cand_kernel(SelectParams sp, const float2 *__restrict__ ws_a, SelCand *__
         else mk |= (i > nts && i <= last_ts);
         return mk;
     };
-    for (int i = lo + tid; i < hi; i += 256) {
-        const float p = expf(x[i] - M) / S, sup = sp.suppress[i];
+#pragma unroll 1
+    for (int i = lo + tid; i < hi; i += nt) {
+        const float p = expf(__ldcg(x + i) - M) / S, sup = sp.suppress[i];
         if (mode_b >= 0) {
             const float ps = p + sup;
             if (i > nts) ts += ps;
@@ -566,39 +590,58 @@ select_cand_kernel(SelectParams sp, const float2 *__restrict__ ws_a, SelCand *__
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
         }
-        __syncthreads();
+        block_sync<BAR, NT>();
         if ((tid & 31) == 0) { red[tid >> 5] = bv; red_i[tid >> 5] = bi; }
-        __syncthreads();
+        block_sync<BAR, NT>();
         if (tid == 0)
-            for (int k = 1; k < 8; ++k)
+#pragma unroll 1
+            for (int k = 1; k < (nt >> 5); ++k)
                 if (red[k] > bv || (red[k] == bv && red_i[k] > bi)) { bv = red[k]; bi = red_i[k]; }
     };
     arg_reduce(ba, ia);
     if (mode_b >= 0) arg_reduce(bb, ib);
-    const float sum_ts = block_sum(ts, red);
-    const float max_text = block_max(mt, red);
-    if (tid == 0) ws_b[b * SEL_CH + c] = SelCand{sum_ts, max_text, ba, bb, ia, ib};
+    const float sum_ts = block_sum<BAR, NT>(ts, red);
+    const float max_text = block_max<BAR, NT>(mt, red);
+    if (tid == 0) ws_b[b * nch + c] = SelCand{sum_ts, max_text, ba, bb, ia, ib};
+}
+__global__ void __launch_bounds__(256)
+select_cand_kernel(SelectParams sp, const float2 *__restrict__ ws_a, SelCand *__restrict__ ws_b) {
+    __shared__ float red[32];
+    __shared__ int red_i[32];
+    select_cand_body(sp, ws_a, ws_b, blockIdx.x, blockIdx.y, SEL_CH, red, red_i);
 }
 
 // phase C: one warp per window folds the chunk results, applies norma's rule and updates the decoding state
-__global__ void __launch_bounds__(32)
-select_final_kernel(SelectParams sp, const SelCand *__restrict__ ws_b) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+// one warp, warp-uniform b; `advance` = this warp also moves the device-resident position to the next step
+__device__ __forceinline__ void select_final_body(const SelectParams &sp, const SelCand *__restrict__ ws_b, int b, int lane, bool advance, int nch) {
     const int max_new = sp.dyn->max_new;
     __syncwarp();
-    if (b == 0 && lane == 0) sp.dyn->pos += 1;
-    if (sp.done[b]) return;
-    const SelCand cd = ws_b[b * SEL_CH + lane];  // SEL_CH == 32: one chunk per lane
+    if (advance && lane == 0) sp.dyn->pos += 1;
+    if (__ldcg(sp.done + b)) return;
+    SelCand cd{0.f, -INFINITY, -INFINITY, -INFINITY, -1, -1};
+#pragma unroll 1
+    for (int c = lane; c < nch; c += 32) {  // chunks of this lane, in ascending order
+        SelCand o;
+        {
+            const float2 *pc = (const float2 *)(ws_b + b * nch + c);
+            const float2 u0 = __ldcg(pc), u1 = __ldcg(pc + 1), u2 = __ldcg(pc + 2);
+            o.sum_ts = u0.x; o.max_text = u0.y; o.best_a = u1.x; o.best_b = u1.y; o.idx_a = __float_as_int(u2.x); o.idx_b = __float_as_int(u2.y);
+        }
+        cd.sum_ts += o.sum_ts;
+        cd.max_text = fmaxf(cd.max_text, o.max_text);
+        if (o.best_a > cd.best_a || (o.best_a == cd.best_a && o.idx_a > cd.idx_a)) { cd.best_a = o.best_a; cd.idx_a = o.idx_a; }
+        if (o.best_b > cd.best_b || (o.best_b == cd.best_b && o.idx_b > cd.idx_b)) { cd.best_b = o.best_b; cd.idx_b = o.idx_b; }
+    }
     float ts = cd.sum_ts, mt = cd.max_text;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ts += __shfl_xor_sync(0xffffffffu, ts, o);
         mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
     }
-    const int len = sp.len[b], last_ts = sp.last_ts[b], nts = (int)sp.nts;
+    const int len = __ldcg(sp.len + b), last_ts = __ldcg(sp.last_ts + b), nts = (int)sp.nts;
     bool use_b = false;
     if (last_ts >= 0) {
-        const uint32_t l_tok = sp.tokens[(size_t)b * sp.max_pos + len - 1];
+        const uint32_t l_tok = __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 1);
         if ((int)l_tok <= nts) use_b = !(ts >= mt);  // sum_prob_timestamp >= prob_non_timestamp -> timestamps only (model.rs:272)
     }
     float best = use_b ? cd.best_b : cd.best_a;
@@ -626,6 +669,11 @@ select_final_kernel(SelectParams sp, const SelCand *__restrict__ ws_b) {
         }
         sp.len[b] = l;
     }
+}
+
+__global__ void __launch_bounds__(32)
+select_final_kernel(SelectParams sp, const SelCand *__restrict__ ws_b) {
+    select_final_body(sp, ws_b, blockIdx.x, threadIdx.x, blockIdx.x == 0, SEL_CH);
 }
 
 // no_speech_prob = softmax(logits at prompt position 0)[no_speech]; > 0.6 ends the window (model.rs:293-315)
@@ -711,6 +759,518 @@ __global__ void set_dyn_kernel(DecodeDyn *dyn, int pos, int max_new, float tempe
 __global__ void copy_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
+}
+
+// =====================================================================================================================
+// Fused decoder step (round 1d, bf16).  One decoder position used to be ~25 kernels (11 weight-streaming GEMVs worth 0.5 - 20 us of
+// HBM time each, 8 attention launches, 3 select launches): at B = 1 the step took 264 us against a 34 us HBM floor, every kernel
+// paying launch, drain and prologue latency.  Here the whole step is ONE cooperative kernel, one CTA per SM:
+//   per layer: LN1+QKV | self-attn | out+res | LNc+q | cross-attn | out+res | LN2+fc1+GELU | fc2+res || LN+logits | stats | cand | final
+// * a producer warp streams every weight matrix of the step, in order, through a 4 x 40 KB shared-memory ring with 1-D bulk copies
+//   (rows of a [N][K] matrix are contiguous: a tile of R rows is one copy, no tensor map).  The weights do not depend on the
+//   activations, so the producer never waits at a grid barrier: while the CTAs synchronise and stage the next phase's input the ring
+//   is already filling with its weights, and HBM keeps streaming across phase boundaries (160 KB in flight per SM).
+// * 16 consumer warps take the tiles out of the ring (one row, or a K-slice of a row, per warp), phases are separated by a grid
+//   barrier (one release-add + acquire-poll on a monotonic counter; cooperative launch guarantees co-residency).
+// * the split-K attention partials are merged by whichever worker finishes a (window, head) last (atomic ticket): no extra barrier.
+// Same arithmetic as the separate kernels (shared device code for attention and select; the GEMV sums in a different order).
+// The phase bodies are __noinline__ on purpose: inlined nine times the kernel was 316 KB of SASS and every phase ran out of a cold
+// instruction cache (the first tile of a phase took 8 us, the following ones 2 us).
+// =====================================================================================================================
+constexpr int FS_WARPS = 16;                    // consumer warps
+constexpr int FS_THREADS = (FS_WARPS + 1) * 32;  // + the producer warp
+constexpr int FS_CTHREADS = FS_WARPS * 32;
+constexpr int FS_MMA_WARPS = 4;                 // consumer warps that run the GEMV tiles (tensor cores: one warp outruns HBM)
+constexpr int FS_STAGES = 4;
+constexpr int FS_ROW_PAD = 16;                  // bytes added to a tile row so that ldmatrix rows fall in different banks
+constexpr int FS_TILE_BYTES = 16 * (SK_KC_MAX * 2 + FS_ROW_PAD);  // 16 weight rows x d_model columns (one K chunk)
+constexpr int FS_XS_BYTES = 40960;              // staged activations in bf16: 8 rows at K <= 2560, 4 rows at K = 5120 (fc2)
+constexpr int FS_OFF_XS = FS_STAGES * FS_TILE_BYTES;
+constexpr int FS_OFF_BAR = FS_OFF_XS + FS_XS_BYTES;
+constexpr int FS_SMEM = FS_OFF_BAR + 2 * FS_STAGES * 8;
+constexpr int FS_BAR_ID = 5;  // named barrier of the 512 consumer threads
+constexpr int FS_SELF_SPLITS = 8, FS_MAX_SPLITS = 64;  // split-K of the decode attention (workspace: FS_MAX_SPLITS partials per window and head)
+
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync %0, %1;" ::"n"(FS_BAR_ID), "n"(FS_CTHREADS) : "memory"); }
+
+// grid barrier over the consumer threads of every CTA: `target` = arrivals expected so far on the monotonic counter
+__device__ __forceinline__ void grid_sync(unsigned *counter, unsigned &target) {
+    cbar();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while ((int)(seen - target) < 0);
+    }
+    cbar();
+}
+
+struct FusedArgs {
+    int B, d, V, P, T, H, L, max_batch;
+    const DecLayer *layers;  // device copy of ctx->dec
+    const bf16 *embed;
+    const float *embed_pos, *lndec_g, *lndec_b;
+    uint32_t *tokens;
+    int *len;
+    DecodeDyn *dyn;
+    float *dx, *dqkv, *dattn, *dq, *dff, *dhid, *logits, *attn_ws;
+    unsigned *attn_cnt;  // [max_batch][H] tickets, zero between uses
+    bf16 *self_kv, *cross_kv;
+    SelectParams sp;
+    float2 *sel_a;
+    SelCand *sel_b;
+    unsigned *sync_counter;
+    unsigned *sync_epoch;  // value the counter has when a launch starts: read by everyone at entry, advanced by CTA 0 at exit (no host-side
+                           // argument changes between steps, so a step can be replayed from a CUDA graph)
+    int n_steps;         // decoder positions handled by this launch (the CTAs stay resident: starting 148 CTAs of 206 KB costs ~60 us)
+    int cross_splits;    // split-K of the cross attention: enough (window, head, split) items for every warp of the grid
+    float qscale;
+    unsigned long long *tdbg;  // NB200_DECODE_TIMING: %globaltimer of CTA 0 after every phase
+};
+
+#ifdef NB200_DECODE_TIMING
+#define DEC_STAMP() do { if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); a.tdbg[stamp_i] = t_; a.tdbg[32 + stamp_i] = (unsigned long long)clock64(); ++stamp_i; } } while (0)
+#define DEC_CLK(x) x = clock64()
+#define DEC_FINE(tag) do { if (a.tdbg && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); const unsigned long long k_ = a.tdbg[63]; if (k_ < 400) { a.tdbg[64 + 2 * k_] = t_; a.tdbg[65 + 2 * k_] = (tag); a.tdbg[63] = k_ + 1; } } } while (0)
+#else
+#define DEC_STAMP()
+#define DEC_FINE(tag)
+#define DEC_CLK(x)
+#endif
+
+// the weight matrices of one step in streaming order: 6 per layer, then the tied embedding
+struct FsJob { const bf16 *W; int N, K; };
+__device__ __forceinline__ FsJob fs_job(const FusedArgs &a, int j) {
+    const int d = a.d;
+    if (j == 6 * a.L) return FsJob{a.embed, a.V, d};
+    const DecLayer &w = a.layers[j / 6];
+    switch (j % 6) {
+        case 0: return FsJob{(const bf16 *)w.wqkv, 3 * d, d};
+        case 1: return FsJob{(const bf16 *)w.wo, d, d};
+        case 2: return FsJob{(const bf16 *)w.cwq, d, d};
+        case 3: return FsJob{(const bf16 *)w.cwo, d, d};
+        case 4: return FsJob{(const bf16 *)w.w1, 4 * d, d};
+        default: return FsJob{(const bf16 *)w.w2, d, 4 * d};
+    }
+}
+__device__ __forceinline__ int fs_row_cap(int K) { return min(SK_MB, FS_XS_BYTES / (2 * K)); }  // activation rows staged per pass
+
+// producer: every tile this CTA will consume, in consumption order.  A tile = 16 consecutive weight rows x one K chunk of d_model
+// columns; rows are copied one by one (2 d_model bytes each) to a padded pitch so that ldmatrix is bank-conflict free.
+__device__ __noinline__ void fs_produce(const FusedArgs &a, uint32_t ring, uint32_t full0, uint32_t empty0, volatile int *go) {
+    unsigned cnt = 0;
+    const int KC = a.d;
+    const uint32_t pitch = (uint32_t)KC * 2 + FS_ROW_PAD;
+#pragma unroll 1
+    for (int step = 0; step < a.n_steps; ++step) {
+        // the consumers decide after the previous step's select whether there is another step (every window done: stop); no tile of a
+        // step is requested before that, so nothing is in flight when the CTA exits
+        int g;
+        while ((g = *go) <= step && g >= 0) __nanosleep(64);
+        if (g < 0) return;
+#pragma unroll 1
+        for (int j = 0; j <= 6 * a.L; ++j) {
+            const FsJob job = fs_job(a, j);
+            const int n_groups = (job.N + 15) / 16, n_chunks = job.K / KC;
+            const int cap = fs_row_cap(job.K), passes = (a.B + cap - 1) / cap;
+#pragma unroll 1
+            for (int p = 0; p < passes; ++p)
+#pragma unroll 1
+                for (int t = blockIdx.x; t < n_groups; t += gridDim.x)
+#pragma unroll 1
+                    for (int c = 0; c < n_chunks; ++c, ++cnt) {
+                        const unsigned s = cnt % FS_STAGES;
+                        if (cnt >= FS_STAGES) ptx::mbar_wait(empty0 + 8 * s, ((cnt / FS_STAGES) & 1) ^ 1);
+                        const int rows = min(16, job.N - t * 16);
+                        ptx::mbar_expect_tx(full0 + 8 * s, (uint32_t)rows * KC * 2);
+                        const bf16 *src = job.W + (size_t)t * 16 * job.K + (size_t)c * KC;
+#pragma unroll 1
+                        for (int r = 0; r < rows; ++r) ptx::bulk_load_1d(ring + s * FS_TILE_BYTES + r * pitch, src + (size_t)r * job.K, (uint32_t)KC * 2, full0 + 8 * s);
+                    }
+        }
+    }
+}
+
+// rows [0, Bd) of the phase input -> xs[Bd][K] in bf16 (the B operand of the tensor-core GEMV).  ln_g != nullptr: LayerNorm over the
+// row (K = d_model); from_tokens: the row is the embedding of the token at `pos` plus the positional row (first phase of the step;
+// CTA 0 also leaves it in dx for the residual).  Everything here is a rolled loop on purpose: this code runs once per phase, and
+// straight-line code that runs once is fetched from L2 line by line (an unrolled register-resident version took 30 us).
+__device__ __noinline__ void fs_stage(const FusedArgs &a, const float *__restrict__ x, int ldx, int K, int m_first, int Bd, const float *__restrict__ ln_g,
+                                      const float *__restrict__ ln_b, float *__restrict__ ln_out, bool from_tokens, int pos, bf16 *xs, float *stats) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cbar();  // the previous phase is done with xs
+    if (!ln_g) {
+#pragma unroll 1
+        for (int i = tid * 4; i < Bd * K; i += FS_CTHREADS * 4) {
+            const int m = i / K, k = i - m * K;
+            const float4 t = __ldcg((const float4 *)(x + (size_t)m * ldx + k));  // written by other SMs during this launch: L2, not L1
+            __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
+            *(uint2 *)&xs[i] = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
+        }
+        cbar();
+        return;
+    }
+    // LayerNorm, four rows at a time: f32 copy of the rows in the upper half of the staging buffer, bf16 result in the lower half
+    float *tmp = (float *)((uint8_t *)xs + FS_XS_BYTES / 2);
+#pragma unroll 1
+    for (int r0 = 0; r0 < Bd; r0 += 4) {
+        const int nb = min(4, Bd - r0);
+#pragma unroll 1
+        for (int i = tid; i < nb * K; i += FS_CTHREADS) {
+            const int m = i / K, k = i - m * K, b = m_first + r0 + m;
+            float t;
+            if (from_tokens) {
+                uint32_t tok = pos < __ldcg(a.len + b) ? __ldcg(a.tokens + (size_t)b * a.P + pos) : 0u;
+                if (tok >= (uint32_t)a.V) tok = 0;
+                t = __bfloat162float(a.embed[(size_t)tok * K + k]) + a.embed_pos[(size_t)pos * K + k];
+                if (blockIdx.x == 0) a.dx[(size_t)b * K + k] = t;
+            } else {
+                t = __ldcg(x + (size_t)(r0 + m) * ldx + k);
+            }
+            tmp[i] = t;
+        }
+        cbar();
+        if (warp < nb) {  // candle_nn LayerNorm: mean, then the centred variance, eps 1e-5
+            const float *row = tmp + warp * K;
+            float s1 = 0.f, s1b = 0.f, s1c = 0.f, s1d = 0.f;  // four independent chains: the loop is latency-, not throughput-bound
+            int k = lane;
+#pragma unroll 1
+            for (; k + 96 < K; k += 128) { s1 += row[k]; s1b += row[k + 32]; s1c += row[k + 64]; s1d += row[k + 96]; }
+#pragma unroll 1
+            for (; k < K; k += 32) s1 += row[k];
+            s1 = (s1 + s1b) + (s1c + s1d);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            const float mean = s1 / (float)K;
+            float s2 = 0.f, s2b = 0.f, s2c = 0.f, s2d = 0.f;
+            k = lane;
+#pragma unroll 1
+            for (; k + 96 < K; k += 128) {
+                const float d0 = row[k] - mean, d1 = row[k + 32] - mean, d2 = row[k + 64] - mean, d3 = row[k + 96] - mean;
+                s2 += d0 * d0; s2b += d1 * d1; s2c += d2 * d2; s2d += d3 * d3;
+            }
+#pragma unroll 1
+            for (; k < K; k += 32) {
+                const float dv = row[k] - mean;
+                s2 += dv * dv;
+            }
+            s2 = (s2 + s2b) + (s2c + s2d);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) {
+                stats[2 * warp] = mean;
+                stats[2 * warp + 1] = rsqrtf(s2 / (float)K + 1e-5f);
+            }
+        }
+        cbar();
+#pragma unroll 1
+        for (int i = tid; i < nb * K; i += FS_CTHREADS) {
+            const int m = i / K, k = i - m * K;
+            const float y = (tmp[i] - stats[2 * m]) * stats[2 * m + 1] * __ldg(ln_g + k) + __ldg(ln_b + k);
+            xs[(r0 + m) * K + k] = __float2bfloat16(y);
+            if (ln_out && blockIdx.x == 0) ln_out[(size_t)(r0 + m) * K + k] = y;
+        }
+        cbar();
+    }
+}
+
+// consumer side of one weight matrix: out[m][n] = epilogue(sum_k x[m][k] W[n][k]) for every window row, on the tensor cores:
+// D[16 weight rows][8 window rows] += A[16 x 16 from the ring tile, ldmatrix] . B[16 x 8 from xs] (mma.sync m16n8k16, fp32 accumulate).
+// The activations are rounded to bf16 like every other GEMM input of the bf16 build.  A 16-row group (all its K chunks) belongs to
+// one of FS_MMA_WARPS warps; the first version did this with FFMA on 16 warps and spent ~300 issue slots per weight row, more than
+// the 0.9 us a 40 KB tile takes to arrive from HBM.
+__device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, int ldx, const float *ln_g, const float *ln_b, float *ln_out, bool from_tokens,
+                                     int pos, SkinnyEpi e, uint8_t *smem, uint32_t full0, uint32_t empty0, unsigned &cnt, float *stats) {
+    const FsJob job = fs_job(a, j);
+    const int K = job.K, N = job.N, KC = a.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_groups = (N + 15) / 16, n_chunks = K / KC, cap = fs_row_cap(K);
+    const uint32_t pitch = (uint32_t)KC * 2 + FS_ROW_PAD;
+    bf16 *xs = (bf16 *)(smem + FS_OFF_XS);
+    const uint32_t ring = ptx::smem_u32(smem);
+#pragma unroll 1
+    for (int m0 = 0; m0 < a.B; m0 += cap) {
+        const int Bd = min(cap, a.B - m0);
+        fs_stage(a, x ? x + (size_t)m0 * ldx : nullptr, ldx, K, m0, Bd, ln_g, ln_b, ln_out ? ln_out + (size_t)m0 * K : nullptr, from_tokens, pos, xs, stats);
+        int gi = 0;
+#pragma unroll 1
+        for (int t = blockIdx.x; t < n_groups; t += gridDim.x, ++gi) {
+            if (warp != (gi % FS_MMA_WARPS)) {  // not this warp's group (warps >= FS_MMA_WARPS own none): just keep the tile count
+                cnt += n_chunks;
+                continue;
+            }
+            float acc[4][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+            // bias and residual of this lane's four outputs, requested now so that their L2 round trips hide behind the MMA loop
+            float ebias[2] = {0.f, 0.f}, eres[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int n = t * 16 + (lane >> 2) + (r >> 1) * 8, m = (lane & 3) * 2 + (r & 1);
+                if (n < N && m < Bd) {
+                    if (e.bias && (r & 1) == 0) ebias[r >> 1] = e.bias[n];
+                    if (e.residual) eres[r] = __ldcg(e.residual + (size_t)(m0 + m) * e.ldr + n);
+                }
+            }
+            const int bn = lane >> 2;  // window row (B operand column) this lane feeds
+            const bf16 *xrow = xs + (bn < Bd ? bn : 0) * K + (lane & 3) * 2;
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; ++c, ++cnt) {
+                const unsigned s = cnt % FS_STAGES;
+                ptx::mbar_wait(full0 + 8 * s, (cnt / FS_STAGES) & 1);
+                const uint32_t arow = ring + s * FS_TILE_BYTES + (lane & 15) * pitch + (lane >> 4) * 16;
+                const bf16 *xk = xrow + c * KC;
+#pragma unroll 4
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                    uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
+                    if (bn < Bd) {
+                        b0 = *(const uint32_t *)(xk + ks * 16);
+                        b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+                    }
+                    float *d = acc[ks & 3];
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(empty0 + 8 * s);  // the tile has been read: the stage can be refilled
+            }
+            // D fragment: rows lane / 4 and lane / 4 + 8 of the group, window rows 2 (lane % 4) and 2 (lane % 4) + 1
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float v = acc[0][r] + acc[1][r] + acc[2][r] + acc[3][r];
+                const int n = t * 16 + (lane >> 2) + (r >> 1) * 8, m = (lane & 3) * 2 + (r & 1);
+                if (n < N && m < Bd) {
+                    v += ebias[r >> 1];
+                    if (n < e.n_scale) v *= e.scale;
+                    if (e.act) v = gelu_tanh_precise(v);
+                    v += eres[r];
+                    e.out[(size_t)(m0 + m) * e.ldo + n] = v;
+                }
+            }
+        }
+    }
+}
+
+// Split-K single-query attention of the fused step: one (head, window, split) item per WARP.  A lane owns two of the 64 head
+// dimensions, so a K (or V) row is one coalesced 128-byte access; the warp walks the keys of its split two at a time with an online
+// softmax, writes (m, l, o[64]) to the workspace, and the warp that takes the last ticket of a (window, head) folds the S partials
+// into `out` (no grid barrier between the splits and the merge).  Rolled loops, ~2 KB of code: the 128-thread version shared with the
+// stand-alone kernels was 17 KB that each phase executed once, out of a cold instruction cache.
+__device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int H, int B, int n_keys, bool append,
+                                     const float *__restrict__ newkv, int ldkv, int koff, int voff, float *__restrict__ ws, unsigned *__restrict__ cnt, int S,
+                                     float *__restrict__ out, int ldo) {
+    const int lane = threadIdx.x & 31, gw = blockIdx.x * FS_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * FS_WARPS;
+    const int n_items = H * B * S;
+#pragma unroll 1
+    for (int it = gw; it < n_items; it += n_warps) {
+        const int sp = it % S, h = (it / S) % H, b = it / (S * H);
+        const int chunk = (n_keys + S - 1) / S, k0 = sp * chunk;
+        int k1 = min(n_keys, k0 + chunk);
+        bf16 *cb = cache + (size_t)b * Tmax * 2 * d + h * HEAD_DIM + lane * 2;
+        const float2 qv = __ldcg((const float2 *)(q + (size_t)b * ldq + h * HEAD_DIM + lane * 2));
+        float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+        int j = k0;
+        if (append && k1 == n_keys && k1 > k0) {  // this split owns the position being decoded: k, v come from the QKV GEMV and join the cache
+            const int jn = n_keys - 1;
+            const float2 kf = __ldcg((const float2 *)(newkv + (size_t)b * ldkv + koff + h * HEAD_DIM + lane * 2));
+            const float2 vf = __ldcg((const float2 *)(newkv + (size_t)b * ldkv + voff + h * HEAD_DIM + lane * 2));
+            const __nv_bfloat162 kb = __floats2bfloat162_rn(kf.x, kf.y), vb = __floats2bfloat162_rn(vf.x, vf.y);
+            *(__nv_bfloat162 *)(cb + (size_t)jn * 2 * d) = kb;
+            *(__nv_bfloat162 *)(cb + (size_t)jn * 2 * d + d) = vb;
+            const float2 kr = __bfloat1622float2(kb), vr = __bfloat1622float2(vb);  // what every later step will read
+            float sd = qv.x * kr.x + qv.y * kr.y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+            m = sd; l = 1.f; a0 = vr.x; a1 = vr.y;
+            k1 = jn;  // the loop below covers the cached keys only
+        }
+        // two keys per iteration; the next pair's K / V rows are requested before this pair's softmax chain (L2 latency ~ the chain)
+        __nv_bfloat162 kA, vA, kB, vB;
+        auto load_pair = [&](int jj) {
+            const int j2 = jj + 1 < k1 ? jj + 1 : jj;
+            kA = *(const __nv_bfloat162 *)(cb + (size_t)jj * 2 * d);
+            vA = *(const __nv_bfloat162 *)(cb + (size_t)jj * 2 * d + d);
+            kB = *(const __nv_bfloat162 *)(cb + (size_t)j2 * 2 * d);
+            vB = *(const __nv_bfloat162 *)(cb + (size_t)j2 * 2 * d + d);
+        };
+        if (j < k1) load_pair(j);
+#pragma unroll 1
+        for (; j < k1; j += 2) {
+            const bool two = j + 1 < k1;
+            const float2 kAf = __bfloat1622float2(kA), kBf = __bfloat1622float2(kB), vAf = __bfloat1622float2(vA), vBf = __bfloat1622float2(vB);
+            if (j + 2 < k1) load_pair(j + 2);
+            float sA = qv.x * kAf.x + qv.y * kAf.y, sB = qv.x * kBf.x + qv.y * kBf.y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                sA += __shfl_xor_sync(0xffffffffu, sA, o);
+                sB += __shfl_xor_sync(0xffffffffu, sB, o);
+            }
+            if (!two) sB = -INFINITY;
+            const float mn = fmaxf(m, fmaxf(sA, sB));
+            const float al = expf(m - mn), pA = expf(sA - mn), pB = expf(sB - mn);  // m = -inf on the first pair: al = 0
+            l = l * al + pA + pB;
+            a0 = a0 * al + pA * vAf.x + pB * vBf.x;
+            a1 = a1 * al + pA * vAf.y + pB * vBf.y;
+            m = mn;
+        }
+        float *wsb = ws + ((size_t)b * H + h) * S * ATT_WS;
+        {
+            float *o = wsb + (size_t)sp * ATT_WS;
+            if (lane == 0) { o[0] = m; o[1] = l; }
+            *(float2 *)(o + 2 + lane * 2) = make_float2(a0, a1);
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = atomicAdd(cnt + b * H + h, 1u) == (unsigned)(S - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // every split of this (window, head) has landed: fold them
+            __threadfence();
+            // lane s holds (m, l) of splits s, s + 32: the weights 2^(m_s - M) come out of two shuffles per split, and the S loads of
+            // the partial outputs below do not depend on each other
+            float m_a = -INFINITY, l_a = 0.f, m_b = -INFINITY, l_b = 0.f;
+            if (lane < S) { m_a = __ldcg(wsb + lane * ATT_WS); l_a = __ldcg(wsb + lane * ATT_WS + 1); }
+            if (lane + 32 < S) { m_b = __ldcg(wsb + (lane + 32) * ATT_WS); l_b = __ldcg(wsb + (lane + 32) * ATT_WS + 1); }
+            float M = fmaxf(m_a, m_b);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+            const float w_a = m_a == -INFINITY ? 0.f : expf(m_a - M), w_b = m_b == -INFINITY ? 0.f : expf(m_b - M);  // empty splits weigh nothing
+            float ll = l_a * w_a + l_b * w_b;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ll += __shfl_xor_sync(0xffffffffu, ll, o);
+            float o0 = 0.f, o1 = 0.f;
+#pragma unroll 16
+            for (int s2 = 0; s2 < S; ++s2) {
+                const float al = __shfl_sync(0xffffffffu, s2 < 32 ? w_a : w_b, s2 & 31);
+                const float2 ov = __ldcg((const float2 *)(wsb + s2 * ATT_WS + 2 + lane * 2));
+                o0 += ov.x * al;
+                o1 += ov.y * al;
+            }
+            *(float2 *)(out + (size_t)b * ldo + h * HEAD_DIM + lane * 2) = make_float2(o0 / ll, o1 / ll);
+            if (lane == 0) cnt[b * H + h] = 0;  // ticket back to zero for the next attention of this launch
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FS_THREADS, 1)
+decoder_step_fused_kernel(const FusedArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ float red[32];
+    __shared__ int red_i[32];
+    __shared__ float ln_stats[32];
+    __shared__ volatile int go_step;
+    const int tid = threadIdx.x;
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t full0 = sbase + FS_OFF_BAR, empty0 = full0 + 8 * FS_STAGES;
+    if (tid == 0) {
+        for (int s = 0; s < FS_STAGES; ++s) {
+            ptx::mbar_init(full0 + 8 * s, 1);
+            ptx::mbar_init(empty0 + 8 * s, 1);
+        }
+        ptx::fence_barrier_init();
+        go_step = 0;
+    }
+    __syncthreads();
+    if (tid >= FS_CTHREADS) {  // producer warp: free-running inside a step, never at a grid barrier
+        if (tid == FS_CTHREADS) fs_produce(a, sbase, full0, empty0, &go_step);
+        return;
+    }
+    int stamp_i = 0;
+    (void)stamp_i;
+    const int d = a.d, B = a.B, V = a.V, P = a.P, T = a.T, H = a.H;
+    const int nch = gridDim.x;  // vocabulary chunks per window in the select: one per CTA
+    unsigned cnt = 0, target = __ldcg(a.sync_epoch);
+#pragma unroll 1
+    for (int step = 0; step < a.n_steps; ++step) {
+    if (step > 0) grid_sync(a.sync_counter, target);  // the previous step's tokens, lengths, done flags and position are visible
+    bool all_done = true;
+#pragma unroll 1
+    for (int b = 0; b < B; ++b) all_done &= __ldcg(a.sp.done + b) != 0;
+    const int pos = __ldcg(&a.dyn->pos);
+    if (all_done || pos >= P) {  // grid-uniform: every CTA reads the same flags after the same barrier
+        if (tid == 0) go_step = -1;
+        break;
+    }
+    if (tid == 0) go_step = step + 1;
+    stamp_i = 0;
+    DEC_STAMP();
+    for (int l = 0; l < a.L; ++l) {
+        const DecLayer w = a.layers[l];
+        bf16 *skv = a.self_kv + (size_t)l * a.max_batch * P * 2 * d;
+        bf16 *ckv = a.cross_kv + (size_t)l * a.max_batch * T * 2 * d;
+        SkinnyEpi e{};
+        e.bias = w.bqkv; e.out = a.dqkv; e.ldo = 3 * d; e.scale = a.qscale; e.n_scale = 2 * d;
+        fs_gemv(a, 6 * l + 0, l == 0 ? nullptr : a.dx, d, w.ln1g, w.ln1b, nullptr, l == 0, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        fs_attn(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, d);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        e = SkinnyEpi{};
+        e.bias = w.bo; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
+        fs_gemv(a, 6 * l + 1, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        e = SkinnyEpi{};
+        e.bias = w.cbq; e.out = a.dq; e.ldo = d; e.scale = a.qscale; e.n_scale = d;
+        fs_gemv(a, 6 * l + 2, a.dx, d, w.lncg, w.lncb, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        fs_attn(a.dq, d, ckv, T, d, H, B, T, false, nullptr, 0, 0, 0, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn, d);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        e = SkinnyEpi{};
+        e.bias = w.cbo; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
+        fs_gemv(a, 6 * l + 3, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        e = SkinnyEpi{};
+        e.bias = w.b1; e.out = a.dff; e.ldo = 4 * d; e.act = 1;
+        fs_gemv(a, 6 * l + 4, a.dx, d, w.ln2g, w.ln2b, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+        e = SkinnyEpi{};
+        e.bias = w.b2; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
+        fs_gemv(a, 6 * l + 5, a.dff, 4 * d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        grid_sync(a.sync_counter, target);
+        DEC_STAMP();
+    }
+    {   // final LayerNorm fused into the tied-embedding logits; CTA 0 leaves the hidden state in dhid
+        SkinnyEpi e{};
+        e.out = a.logits; e.ldo = V;
+        fs_gemv(a, 6 * a.L, a.dx, d, a.lndec_g, a.lndec_b, a.dhid, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+    }
+    grid_sync(a.sync_counter, target);
+    DEC_STAMP();
+    // ---- greedy select (the three phases of select_*_kernel; FS_CTHREADS threads through the consumers' named barrier) ----
+#pragma unroll 1
+    for (int it = blockIdx.x; it < B * nch; it += gridDim.x) {
+        cbar();
+        select_stats_body<FS_BAR_ID, FS_CTHREADS>(a.logits, V, a.sel_a, it / nch, it % nch, nch, red);
+    }
+    grid_sync(a.sync_counter, target);
+    DEC_STAMP();
+#pragma unroll 1
+    for (int it = blockIdx.x; it < B * nch; it += gridDim.x) {
+        cbar();
+        select_cand_body<FS_BAR_ID, FS_CTHREADS>(a.sp, a.sel_a, a.sel_b, it / nch, it % nch, nch, red, red_i);
+    }
+    grid_sync(a.sync_counter, target);
+    DEC_STAMP();
+    if (tid < 32)
+        for (int b = blockIdx.x; b < B; b += gridDim.x) select_final_body(a.sp, a.sel_b, b, tid, b == 0, nch);
+    DEC_STAMP();
+    }  // step
+    if (blockIdx.x == 0 && tid == 0) *a.sync_epoch = target;  // every CTA read the old value before its first barrier
+#ifdef NB200_DECODE_TIMING
+    if (a.tdbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); atomicMax(a.tdbg + 52, t_); }
+#endif
 }
 
 }  // namespace
@@ -901,6 +1461,86 @@ int decoder_select(nb200_ctx *ctx, int n_windows, int greedy) {
         decode_select_kernel<<<n_windows, 1024, 0, ctx->stream>>>(sp);
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    return NB200_OK;
+}
+
+// n_steps greedy decoder steps for windows [0, n_windows) as a single cooperative launch (embed .. logits .. select per step); the
+// position is the device-resident one (DecodeDyn) and advances after every step; the launch ends early once every window is done.
+// bf16 contexts only.
+bool decoder_fused_supported(const nb200_ctx *ctx) {
+    const nb200_config &c = ctx->cfg;
+    return ctx->compute == NB200_BF16 && c.d_model % 16 == 0 && c.d_model <= SK_KC_MAX && c.decoder_attention_heads * HEAD_DIM == c.d_model;
+}
+
+int decoder_fused_ws_floats(const nb200_ctx *ctx) { return ctx->cfg.max_batch * ctx->cfg.decoder_attention_heads * FS_MAX_SPLITS * ATT_WS; }
+
+// one-time sizing of the cooperative grid and its workspaces (not capturable: called before any graph capture of the step)
+int decoder_fused_prepare(nb200_ctx *ctx) {
+    const nb200_config &c = ctx->cfg;
+    if (!decoder_fused_supported(ctx)) return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "fused decoder step: d_model=%d, compute=%d", c.d_model, (int)ctx->compute);
+    if (ctx->fused_ctas != 0) return NB200_OK;
+    void *kern = (void *)decoder_step_fused_kernel;
+    int per_sm = 0;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FS_THREADS, FS_SMEM));
+    if (per_sm < 1) return nb200_fail(ctx, NB200_CUDA_ERROR, "fused decoder step does not fit an SM");
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_fused_sel_ws, (size_t)c.max_batch * ctx->sm_count * (sizeof(float2) + sizeof(SelCand))));
+    ctx->allocs.push_back(ctx->d_fused_sel_ws);
+    ctx->fused_ctas = ctx->sm_count;  // one CTA per SM; the cooperative launch fails rather than hangs if they cannot all be resident
+    return NB200_OK;
+}
+
+int decoder_step_fused(nb200_ctx *ctx, int n_windows, int n_steps) {
+    const nb200_config &c = ctx->cfg;
+    NB_TRY(decoder_fused_prepare(ctx));
+    void *kern = (void *)decoder_step_fused_kernel;
+    FusedArgs a{};
+    a.B = n_windows; a.d = c.d_model; a.V = c.vocab_size; a.P = c.max_target_positions; a.T = c.max_source_positions;
+    a.H = c.decoder_attention_heads; a.L = c.decoder_layers; a.max_batch = c.max_batch;
+    a.layers = (const DecLayer *)ctx->d_dec_layers;
+    a.embed = (const bf16 *)ctx->embed; a.embed_pos = ctx->embed_pos; a.lndec_g = ctx->lndec_g; a.lndec_b = ctx->lndec_b;
+    a.tokens = ctx->d_tokens; a.len = ctx->d_len; a.dyn = (DecodeDyn *)ctx->d_dyn;
+    a.dx = ctx->dx; a.dqkv = ctx->dqkv; a.dattn = ctx->dattn; a.dq = ctx->dq; a.dff = ctx->dff; a.dhid = ctx->dhid; a.logits = ctx->logits;
+    a.attn_ws = ctx->d_fused_attn_ws; a.attn_cnt = (unsigned *)ctx->d_fused_sync + 32;
+    a.cross_splits = std::max(1, std::min(FS_MAX_SPLITS, (ctx->fused_ctas * FS_WARPS) / std::max(1, n_windows * c.decoder_attention_heads)));
+    a.self_kv = (bf16 *)ctx->self_kv; a.cross_kv = (bf16 *)ctx->cross_kv;
+    SelectParams &sp = a.sp;
+    sp.logits = ctx->logits; sp.suppress = ctx->suppress; sp.tokens = ctx->d_tokens;
+    sp.len = ctx->d_len; sp.last_ts = ctx->d_last_ts; sp.done = ctx->d_done; sp.nsampled = ctx->d_nsampled; sp.sumlp = ctx->d_sumlp;
+    sp.V = c.vocab_size; sp.max_pos = c.max_target_positions; sp.dyn = (DecodeDyn *)ctx->d_dyn;
+    sp.eot = ctx->tok.eot; sp.nts = ctx->tok.no_timestamps; sp.ts_zero = ctx->tok.ts_zero; sp.ts_one = ctx->tok.ts_one;
+    a.sel_a = (float2 *)ctx->d_fused_sel_ws;
+    a.sel_b = (SelCand *)((float2 *)ctx->d_fused_sel_ws + (size_t)c.max_batch * ctx->fused_ctas);
+    a.sync_counter = (unsigned *)ctx->d_fused_sync;
+    a.n_steps = n_steps;
+    a.sync_epoch = (unsigned *)ctx->d_fused_sync + 16;  // its own 64 B, away from the counter's line
+    a.qscale = powf((float)HEAD_DIM, -0.25f);
+#ifdef NB200_DECODE_TIMING
+    static unsigned long long *tdbg = nullptr;
+    if (!tdbg) cudaMalloc(&tdbg, 1024 * 8);
+    cudaMemsetAsync(tdbg + 63, 0, 8, ctx->stream);
+    cudaMemsetAsync(tdbg + 50, 0xff, 8, ctx->stream);
+    cudaMemsetAsync(tdbg + 51, 0, 16, ctx->stream);
+    a.tdbg = tdbg;
+#endif
+    KernelScope ks(ctx, NB200_K_DECODE_GEMV);
+    void *args[] = {(void *)&a};
+    CUDA_TRY(ctx, cudaLaunchCooperativeKernel(kern, dim3(ctx->fused_ctas), dim3(FS_THREADS), args, FS_SMEM, ctx->stream));
+#ifdef NB200_DECODE_TIMING
+    {
+        static int calls = 0;
+        if (++calls % 4 == 0) {
+            unsigned long long h[1024];
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(h, tdbg, sizeof h, cudaMemcpyDeviceToHost);
+            const int n = 1 + 8 * c.decoder_layers + 4;
+            fprintf(stderr, "[fused step] phases (us):");
+            for (int i = 1; i < n; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[i - 1]) * 1e-3);
+            fprintf(stderr, " | CTA starts spread over %.1f us, first start -> last end %.1f us", (double)(h[51] - h[50]) * 1e-3, (double)(h[52] - h[50]) * 1e-3);
+            fprintf(stderr, " | total %.1f us, SM clock %.0f MHz\n", (double)(h[n - 1] - h[0]) * 1e-3, (double)(h[32 + n - 1] - h[32]) / ((double)(h[n - 1] - h[0]) * 1e-3));
+        }
+    }
+#endif
     return NB200_OK;
 }
 

@@ -77,6 +77,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, uint32_t src,
                  "r"(src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map): `bytes` (multiple of 16) contiguous bytes, completion counted on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {  // at most N groups still READING their smem source
