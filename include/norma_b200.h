@@ -217,6 +217,12 @@ NB200_API int nb200_tokenizer_language_tokens(const nb200_tokenizer *t, uint32_t
 /* replaces `VarBuilder::from_mmaped_safetensors(&[weights_file], m::DTYPE, &device)` (monolingual.rs:371-372): mmaps the file and
  * hands every `model.*` tensor (F32 / F16 / BF16 / F64, converted to f32 like candle) to nb200_load_tensor; finalize separately */
 NB200_API int nb200_load_safetensors(nb200_ctx *ctx, const char *path, size_t *n_tensors);
+/* replaces `quantized_var_builder::VarBuilder::from_gguf` + `quantized_model::Whisper::load` (monolingual.rs:364-369) for the `Quantized*`
+ * model types: GGUF v2 / v3 with F32, F16 and Q8_0 tensors, every `model.*` tensor DEQUANTISED to f32 and handed to nb200_load_tensor (candle
+ * keeps q8_0 weights and quantises activations per block: parity with it is within that quantisation error, see loader.h).
+ * nb200_model_from_files recognises a GGUF weights file by its magic. */
+NB200_API int nb200_load_gguf(nb200_ctx *ctx, const char *path, size_t *n_tensors);
+NB200_API int nb200_gguf_read(const char *path, const char *name, float *out, size_t cap, int64_t *shape, int *rank, int *type);
 /* ctx-less read of one tensor converted to f32 (tests, tools): out (nullable) receives min(cap, numel) values, shape up to 8 dims */
 NB200_API int nb200_safetensors_read(const char *path, const char *name, float *out, size_t cap, int64_t *shape, int *rank);
 /* `transcribe` then detokenizes with the tokenizer (a copy is kept) instead of the nb200_model_set_vocab table */

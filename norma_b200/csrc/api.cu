@@ -922,42 +922,50 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     // greedy steady state: POLL steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 falls back to the
     // ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose sampler is a single-block kernel)
     static const bool fused_ok = [] { const char *e = getenv("NB200_DECODE_FUSED"); return !(e && e[0] == '0'); }();
-    const bool use_fused = greedy && fused_ok && decoder_fused_supported(ctx);
-    const bool use_graph = !use_fused && !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
+    bool use_fused = greedy && fused_ok && !ctx->fused_failed && decoder_fused_supported(ctx);
+    const bool graph_ok = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
     cudaGraphExec_t gexec = nullptr;
-    if (use_graph) {
+    auto ensure_graph = [&]() -> int {
+        if (gexec || !graph_ok) return NB200_OK;
         const int gkey = B * 2 + greedy;
         auto it = ctx->step_graphs.find(gkey);
-        if (it == ctx->step_graphs.end()) {
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-            int st = decoder_step(ctx, 0, B, -1, 1);
-            if (st == NB200_OK) st = decoder_select(ctx, B, greedy);
-            cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-            if (st != NB200_OK) return st;
-            if (ce != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph capture failed: %s", cudaGetErrorString(ce));
-            CUDA_TRY(ctx, cudaGraphInstantiate(&gexec, graph, 0));
-            cudaGraphDestroy(graph);
-            ctx->step_graphs[gkey] = gexec;
-        } else gexec = it->second;
-    }
+        if (it != ctx->step_graphs.end()) { gexec = it->second; return NB200_OK; }
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int st = decoder_step(ctx, 0, B, -1, 1);
+        if (st == NB200_OK) st = decoder_select(ctx, B, greedy);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (st != NB200_OK) return st;
+        if (ce != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph capture failed: %s", cudaGetErrorString(ce));
+        CUDA_TRY(ctx, cudaGraphInstantiate(&gexec, graph, 0));
+        cudaGraphDestroy(graph);
+        ctx->step_graphs[gkey] = gexec;
+        return NB200_OK;
+    };
     const int POLL = 16;
-    if (use_fused) NB_TRY(decoder_fused_prepare(ctx));
+    if (use_fused && decoder_fused_prepare(ctx) != NB200_OK) use_fused = false;
+    if (!use_fused) NB_TRY(ensure_graph());
     for (int pos = plen; pos < P;) {
         CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         bool all = true;
         for (int b = 0; b < B; ++b) all &= done[b] != 0;
         if (all) break;
-        const int n = (use_graph || use_fused) ? std::min(POLL, P - pos) : 1;
+        const int n = (graph_ok || use_fused) ? std::min(POLL, P - pos) : 1;
         if (use_fused) {  // one cooperative launch for the next n positions: the CTAs stay resident between steps
-            NB_TRY(decoder_step_fused(ctx, B, n));
-            pos += n;
-            continue;
+            if (decoder_step_fused(ctx, B, n) == NB200_OK) {
+                pos += n;
+                continue;
+            }
+            // the cooperative launch was refused (e.g. the SMs are shared with another process and 148 CTAs cannot be co-resident):
+            // nothing ran, the decoding state is untouched; this context uses the separate kernels from now on
+            cudaGetLastError();
+            ctx->fused_failed = true;
+            use_fused = false;
+            NB_TRY(ensure_graph());
         }
         for (int i = 0; i < n; ++i) {
-            if (false) {}
-            else if (use_graph) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            if (gexec) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
             else {
                 NB_TRY(decoder_step(ctx, 0, B, -1, 1));
                 NB_TRY(decoder_select(ctx, B, greedy));

@@ -325,6 +325,135 @@ bool Safetensors::open(const std::string &path, std::string *err) {
     return true;
 }
 
+
+// ---- GGUF ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct Cursor {
+    const uint8_t *p, *end;
+    bool ok = true;
+    template <typename T> T get() {
+        T v{};
+        if ((size_t)(end - p) < sizeof(T)) { ok = false; p = end; return v; }
+        memcpy(&v, p, sizeof(T));
+        p += sizeof(T);
+        return v;
+    }
+    std::string str() {
+        const uint64_t n = get<uint64_t>();
+        if (!ok || n > (uint64_t)(end - p)) { ok = false; return std::string(); }
+        std::string s((const char *)p, (size_t)n);
+        p += n;
+        return s;
+    }
+    void skip(uint64_t n) {
+        if (n > (uint64_t)(end - p)) { ok = false; p = end; } else p += n;
+    }
+};
+const int GGUF_SCALAR_SIZE[13] = {1, 1, 2, 2, 4, 4, 4, 1, 0, 0, 8, 8, 8};  // by value type; 8 = string, 9 = array
+
+bool skip_value(Cursor &c, uint32_t type, uint32_t *alignment, bool is_alignment_key) {
+    if (type == 8) { c.str(); return c.ok; }
+    if (type == 9) {
+        const uint32_t et = c.get<uint32_t>();
+        const uint64_t n = c.get<uint64_t>();
+        if (!c.ok || et > 12 || et == 9) return false;
+        if (et == 8) { for (uint64_t i = 0; i < n && c.ok; ++i) c.str(); }
+        else c.skip(n * (uint64_t)GGUF_SCALAR_SIZE[et]);
+        return c.ok;
+    }
+    if (type > 12) return false;
+    if (is_alignment_key && type == 4) { *alignment = c.get<uint32_t>(); return c.ok; }
+    c.skip((uint64_t)GGUF_SCALAR_SIZE[type]);
+    return c.ok;
+}
+
+float half_to_float(uint16_t h) {
+    const uint32_t sign = (h >> 15) & 1u, ex = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    float f;
+    if (ex == 0) f = ldexpf((float)man, -24);
+    else if (ex == 31) f = man ? NAN : INFINITY;
+    else f = ldexpf((float)(man | 0x400u), (int)ex - 25);
+    return sign ? -f : f;
+}
+}  // namespace
+
+Gguf::~Gguf() {
+    if (base_) munmap(base_, size_);
+}
+
+bool Gguf::open(const std::string &path, std::string *err) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) { *err = "cannot open '" + path + "': " + strerror(errno); return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 24) { ::close(fd); *err = "gguf: '" + path + "' is too short"; return false; }
+    size_ = (size_t)st.st_size;
+    void *p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (p == MAP_FAILED) { *err = std::string("gguf: mmap failed: ") + strerror(errno); return false; }
+    base_ = (uint8_t *)p;
+    Cursor c{base_, base_ + size_};
+    if (c.get<uint32_t>() != 0x46554747u) { *err = "gguf: bad magic"; return false; }
+    const uint32_t version = c.get<uint32_t>();
+    if (version != 2 && version != 3) { *err = "gguf: unsupported version " + std::to_string(version); return false; }
+    const uint64_t n_tensors = c.get<uint64_t>(), n_kv = c.get<uint64_t>();
+    if (!c.ok || n_tensors > 1000000 || n_kv > 1000000) { *err = "gguf: implausible header counts"; return false; }
+    uint32_t alignment = 32;
+    for (uint64_t i = 0; i < n_kv; ++i) {
+        const std::string key = c.str();
+        const uint32_t type = c.get<uint32_t>();
+        if (!c.ok || !skip_value(c, type, &alignment, key == "general.alignment")) { *err = "gguf: malformed metadata"; return false; }
+    }
+    if (alignment == 0 || (alignment & (alignment - 1))) { *err = "gguf: alignment is not a power of two"; return false; }
+    for (uint64_t i = 0; i < n_tensors; ++i) {
+        GgufEntry e;
+        e.name = c.str();
+        const uint32_t nd = c.get<uint32_t>();
+        if (!c.ok || nd == 0 || nd > 4) { *err = "gguf: bad rank for tensor " + std::to_string(i); return false; }
+        std::vector<int64_t> dims(nd);
+        e.numel = 1;
+        for (uint32_t k = 0; k < nd; ++k) {
+            const uint64_t dk = c.get<uint64_t>();
+            if (dk == 0 || dk > (1ull << 40)) { *err = "gguf: bad dimension in '" + e.name + "'"; return false; }
+            dims[k] = (int64_t)dk;
+            e.numel *= (size_t)dk;
+        }
+        e.shape.assign(dims.rbegin(), dims.rend());  // innermost-first -> row-major
+        e.type = c.get<uint32_t>();
+        e.offset = (size_t)c.get<uint64_t>();
+        if (!c.ok) { *err = "gguf: truncated tensor table"; return false; }
+        entries_.push_back(std::move(e));
+    }
+    data_off_ = ((size_t)(c.p - base_) + alignment - 1) / alignment * alignment;
+    for (auto &e : entries_) {
+        size_t bytes;
+        if (e.type == 0) bytes = e.numel * 4;
+        else if (e.type == 1) bytes = e.numel * 2;
+        else if (e.type == 8) {
+            if (e.shape.back() % 32) { *err = "gguf: Q8_0 tensor '" + e.name + "' has a row length that is not a multiple of 32"; return false; }
+            bytes = e.numel / 32 * 34;
+        } else { *err = "gguf: tensor '" + e.name + "' has unsupported type " + std::to_string(e.type) + " (F32, F16 and Q8_0 are read)"; return false; }
+        if (data_off_ + e.offset + bytes > size_) { *err = "gguf: tensor '" + e.name + "' runs past the end of the file"; return false; }
+    }
+    return true;
+}
+
+bool Gguf::dequantize(const GgufEntry &e, float *out, std::string *err) const {
+    const uint8_t *src = base_ + data_off_ + e.offset;
+    if (e.type == 0) memcpy(out, src, e.numel * 4);
+    else if (e.type == 1) {
+        for (size_t i = 0; i < e.numel; ++i) { uint16_t h; memcpy(&h, src + 2 * i, 2); out[i] = half_to_float(h); }
+    } else if (e.type == 8) {  // block_q8_0 { f16 d; int8 qs[32]; }: w = d * q
+        for (size_t b = 0; b < e.numel / 32; ++b) {
+            uint16_t h;
+            memcpy(&h, src + 34 * b, 2);
+            const float d = half_to_float(h);
+            const int8_t *q = (const int8_t *)(src + 34 * b + 2);
+            for (int i = 0; i < 32; ++i) out[32 * b + i] = d * (float)q[i];
+        }
+    } else { *err = "gguf: unsupported tensor type"; return false; }
+    return true;
+}
+
 }  // namespace nb200host
 
 // ---------------------------------------------------------------------------------------------------------
@@ -445,6 +574,44 @@ int nb200_load_safetensors(nb200_ctx *ctx, const char *path, size_t *n_tensors) 
     return NB200_OK;
 }
 
+int nb200_load_gguf(nb200_ctx *ctx, const char *path, size_t *n_tensors) {
+    if (!ctx || !path) return nb200_fail(ctx, NB200_INVALID_ARG, "load_gguf: NULL argument");
+    nb200host::Gguf g;
+    std::string err;
+    if (!g.open(path, &err)) return nb200_fail(ctx, err.rfind("cannot open", 0) == 0 ? NB200_IO_ERROR : NB200_PARSE_ERROR, "%s", err.c_str());
+    size_t n = 0;
+    std::vector<float> buf;
+    for (auto &e : g.entries()) {
+        if (e.name.rfind("model.", 0) != 0) continue;
+        buf.resize(e.numel);
+        if (!g.dequantize(e, buf.data(), &err)) return nb200_fail(ctx, NB200_PARSE_ERROR, "%s", err.c_str());
+        int rc = nb200_load_tensor(ctx, e.name.c_str(), buf.data(), NB200_F32, e.shape.data(), (int)e.shape.size());
+        if (rc != NB200_OK) return rc;
+        ++n;
+    }
+    if (n_tensors) *n_tensors = n;
+    return NB200_OK;
+}
+
+int nb200_gguf_read(const char *path, const char *name, float *out, size_t cap, int64_t *shape, int *rank, int *type) {
+    if (!path || !name) return nb200_fail(nullptr, NB200_INVALID_ARG, "gguf_read: NULL argument");
+    nb200host::Gguf g;
+    std::string err;
+    if (!g.open(path, &err)) return nb200_fail(nullptr, err.rfind("cannot open", 0) == 0 ? NB200_IO_ERROR : NB200_PARSE_ERROR, "%s", err.c_str());
+    for (auto &e : g.entries()) {
+        if (e.name != name) continue;
+        if (rank) *rank = (int)e.shape.size();
+        if (type) *type = (int)e.type;
+        for (size_t i = 0; shape && i < e.shape.size(); ++i) shape[i] = e.shape[i];
+        if (out) {
+            if (cap < e.numel) return nb200_fail(nullptr, NB200_INVALID_ARG, "gguf_read: buffer holds %zu of %zu values", cap, e.numel);
+            if (!g.dequantize(e, out, &err)) return nb200_fail(nullptr, NB200_PARSE_ERROR, "%s", err.c_str());
+        }
+        return NB200_OK;
+    }
+    return nb200_fail(nullptr, NB200_NOT_FOUND, "gguf: no tensor named '%s'", name);
+}
+
 int nb200_safetensors_read(const char *path, const char *name, float *out, size_t cap, int64_t *shape, int *rank) {
     if (!path || !name) return nb200_fail(nullptr, NB200_INVALID_ARG, "safetensors_read: NULL argument");
     nb200host::Safetensors st;
@@ -518,7 +685,13 @@ int nb200_model_from_files(int ordinal, const char *config_json, const char *tok
         nb200_tokenizer_destroy(tk);
         return nb200_fail(nullptr, code, "%s", msg.c_str());
     };
-    if ((st = nb200_load_safetensors(ctx, safetensors, nullptr))) return bail(st);                      // monolingual.rs:371-373
+    bool is_gguf = false;  // `Quantized*` model types hand over model-{ext}-q80.gguf instead (monolingual.rs:364-369)
+    {
+        FILE *f = fopen(safetensors, "rb");
+        char magic[4] = {0, 0, 0, 0};
+        if (f) { is_gguf = fread(magic, 1, 4, f) == 4 && !memcmp(magic, "GGUF", 4); fclose(f); }
+    }
+    if ((st = is_gguf ? nb200_load_gguf(ctx, safetensors, nullptr) : nb200_load_safetensors(ctx, safetensors, nullptr))) return bail(st);  // monolingual.rs:364-373
     if ((st = nb200_finalize_weights(ctx))) return bail(st);
     if ((st = nb200_set_mel_filters(ctx, filters.data(), cfg.num_mel_bins))) return bail(st);
     if ((st = nb200_set_tokens(ctx, &tok))) return bail(st);

@@ -69,6 +69,31 @@ private:
     std::vector<SafetensorsEntry> entries_;
 };
 
+// model-{ext}-q80.gguf of the `Quantized*` model types (monolingual.rs:198-203, 364-369): GGUF v2 / v3, tensors of type F32, F16 or
+// Q8_0 (blocks of 32 weights: f16 scale + 32 int8).  Every tensor is DEQUANTISED to f32 at load and then takes the same bf16 path as a
+// safetensors checkpoint.  candle instead keeps the weights in q8_0 and multiplies them with activations quantised to q8 blocks
+// (`QMatMul`): a different arithmetic whose own quantisation noise (~0.4 % per activation block) is larger than the bf16 rounding here,
+// so parity with it is "within its quantisation error", not bit-level.
+struct GgufEntry {
+    std::string name;
+    uint32_t type;               // 0 F32, 1 F16, 8 Q8_0
+    std::vector<int64_t> shape;  // row-major (GGUF stores the dimensions innermost first)
+    size_t offset, numel;
+};
+
+class Gguf {
+public:
+    ~Gguf();
+    bool open(const std::string &path, std::string *err);
+    const std::vector<GgufEntry> &entries() const { return entries_; }
+    bool dequantize(const GgufEntry &e, float *out, std::string *err) const;  // numel floats
+
+private:
+    uint8_t *base_ = nullptr;
+    size_t size_ = 0, data_off_ = 0;
+    std::vector<GgufEntry> entries_;
+};
+
 bool config_from_json(const char *json, size_t n, nb200_config *cfg, std::vector<uint32_t> *suppress, std::string *err);
 bool read_file(const std::string &path, std::string *out, std::string *err);
 bool mel_filterbank(int n_mel, std::vector<float> *out);  // [n_mel][201]; false unless n_mel is 80 or 128 (Error::MelBins)

@@ -33,7 +33,7 @@ SYMBOLS = [
     "nb200_transcode_submit", "nb200_transcode_collect",
     "nb200_detect_language", "nb200_model_set_language_detection", "nb200_model_language", "nb200_model_script_push_language",
     "nb200_config_from_file", "nb200_mel_filters", "nb200_tokenizer_from_file", "nb200_tokenizer_destroy", "nb200_tokenizer_token_to_id",
-    "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read",
+    "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read", "nb200_load_gguf", "nb200_gguf_read",
     "nb200_model_set_tokenizer", "nb200_model_from_files",
 ]
 
@@ -129,6 +129,8 @@ def load_library() -> C.CDLL:
         "nb200_tokenizer_language_tokens": ([p, u32p], i),
         "nb200_load_safetensors": ([p, C.c_char_p, C.POINTER(sz)], i),
         "nb200_safetensors_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i)], i),
+        "nb200_load_gguf": ([p, C.c_char_p, C.POINTER(sz)], i),
+        "nb200_gguf_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i), C.POINTER(i)], i),
         "nb200_model_set_tokenizer": ([p, p], i),
         "nb200_model_from_files": ([i, C.c_char_p, C.c_char_p, C.c_char_p, i, C.c_char_p, i, sz, C.c_uint64, C.POINTER(p), C.POINTER(p)], i),
     }
@@ -188,6 +190,17 @@ def safetensors_read(path: str, name: str) -> np.ndarray:
     out = np.empty(shp, np.float32)
     _ck_global(lib, lib.nb200_safetensors_read(os.fsencode(path), name.encode(), _f32p(out), out.size, None, None))
     return out
+
+
+def gguf_read(path: str, name: str):
+    """One tensor of a GGUF file dequantised to f32 -> (array, ggml type id)."""
+    lib = load_library()
+    shape = (C.c_int64 * 8)()
+    rank, typ = C.c_int(), C.c_int()
+    _ck_global(lib, lib.nb200_gguf_read(os.fsencode(path), name.encode(), None, 0, shape, C.byref(rank), C.byref(typ)))
+    out = np.empty(tuple(int(shape[k]) for k in range(rank.value)), np.float32)
+    _ck_global(lib, lib.nb200_gguf_read(os.fsencode(path), name.encode(), _f32p(out), out.size, None, None, None))
+    return out, typ.value
 
 
 class Tokenizer:
@@ -300,6 +313,14 @@ class Context:
         """`VarBuilder::from_mmaped_safetensors` + `Whisper::load` (monolingual.rs:371-373)."""
         n = C.c_size_t()
         self._ck(self.lib.nb200_load_safetensors(self.h, os.fsencode(path), C.byref(n)))
+        if finalize:
+            self._ck(self.lib.nb200_finalize_weights(self.h))
+        return n.value
+
+    def load_gguf(self, path: str, finalize: bool = True) -> int:
+        """`VarBuilder::from_gguf` + `quantized_model::Whisper::load` (monolingual.rs:364-369), dequantised at load."""
+        n = C.c_size_t()
+        self._ck(self.lib.nb200_load_gguf(self.h, os.fsencode(path), C.byref(n)))
         if finalize:
             self._ck(self.lib.nb200_finalize_weights(self.h))
         return n.value

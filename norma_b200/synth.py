@@ -295,3 +295,56 @@ def write_checkpoint(directory: str, cfg: Dict[str, int], weights: Dict[str, tor
         w["proj_out.weight"] = w["model.decoder.embed_tokens.weight"]  # tied copy some checkpoints carry
     write_safetensors(paths[2], w, {"format": "pt"})
     return tuple(paths)
+
+
+def quantize_q8_0(a: np.ndarray):
+    """ggml `quantize_row_q8_0`: blocks of 32 along the last axis, d = max|x| / 127 stored as f16, q = round(x / d).
+    -> (raw block bytes, the f32 values those blocks dequantise to)."""
+    x = np.ascontiguousarray(a, np.float32).reshape(-1, 32)
+    amax = np.abs(x).max(axis=1)
+    d = (amax / 127.0).astype(np.float32)
+    inv = np.where(d > 0, 1.0 / np.where(d > 0, d, 1.0), 0.0).astype(np.float32)
+    q = np.rint(x * inv[:, None]).astype(np.int8)
+    d16 = d.astype(np.float16)
+    blocks = np.zeros((x.shape[0], 34), np.uint8)
+    blocks[:, :2] = d16.view(np.uint8).reshape(-1, 2)
+    blocks[:, 2:] = q.view(np.uint8)
+    deq = (d16.astype(np.float32)[:, None] * q.astype(np.float32)).reshape(a.shape)
+    return blocks.tobytes(), deq
+
+
+def write_gguf(path: str, tensors: Dict[str, "np.ndarray | torch.Tensor"], version: int = 3, alignment: int = 32):
+    """GGUF like candle's `model-{ext}-q80.gguf`: matrices (rank >= 2, last dimension a multiple of 32) as Q8_0, everything else F32.
+    Returns {name: the f32 values a reader dequantises to}."""
+    import struct
+
+    def gstr(s: str) -> bytes:
+        b = s.encode()
+        return struct.pack("<Q", len(b)) + b
+
+    infos, blobs, deq, off = [], [], {}, 0
+    for name, v in tensors.items():
+        a = np.ascontiguousarray(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, np.float32)
+        if a.ndim >= 2 and a.shape[-1] % 32 == 0:
+            raw, d = quantize_q8_0(a)
+            typ = 8
+        else:
+            raw, d, typ = a.tobytes(), a, 0
+        deq[name] = d
+        pad = (-len(raw)) % alignment
+        infos.append((name, a.shape, typ, off))
+        blobs.append(raw + b"\0" * pad)
+        off += len(raw) + pad
+    kv = gstr("general.architecture") + struct.pack("<I", 8) + gstr("whisper")
+    kv += gstr("general.alignment") + struct.pack("<II", 4, alignment)
+    kv += gstr("test.array") + struct.pack("<IIQ", 9, 5, 3) + struct.pack("<iii", 1, 2, 3)
+    kv += gstr("test.strings") + struct.pack("<IIQ", 9, 8, 2) + gstr("a") + gstr("bc")
+    head = struct.pack("<IIQQ", 0x46554747, version, len(infos), 4) + kv
+    for name, shape, typ, o in infos:
+        head += gstr(name) + struct.pack("<I", len(shape)) + b"".join(struct.pack("<Q", int(x)) for x in reversed(shape)) + struct.pack("<IQ", typ, o)
+    head += b"\0" * ((-len(head)) % alignment)
+    with open(path, "wb") as f:
+        f.write(head)
+        for b in blobs:
+            f.write(b)
+    return deq

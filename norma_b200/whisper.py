@@ -240,7 +240,7 @@ class Definition:
         if self.device.kind != "cuda":
             raise WhisperError("this build only implements SelectedDevice::Cuda(ord) (sm_100a, no CPU fallback)")
         if self.model.quantized_ext() is not None:
-            raise WhisperError("quantized (q8_0) checkpoints are out of scope for the B200 path")
+            raise WhisperError("quantized (q8_0) checkpoints are loaded from their GGUF file: use blocking_try_to_model_from_files")
         cfg = synth.model_config(self.model.shape())
         ctx = ffi.Context(cfg, ordinal=self.device.ordinal, compute=compute, max_batch=1)
         ctx.set_mel_filters(filters.mel_filters(cfg["num_mel_bins"]))  # Error::MelBins for anything but 80 | 128
@@ -259,8 +259,8 @@ class Definition:
         three files on disk (parsing, upload, token-id lookups, masks), done natively by nb200_model_from_files."""
         if self.device.kind != "cuda":
             raise WhisperError("this build only implements SelectedDevice::Cuda(ord) (sm_100a, no CPU fallback)")
-        if self.model.quantized_ext() is not None:
-            raise WhisperError("quantized (q8_0) checkpoints are out of scope for the B200 path")
+        # `Quantized*` model types pass config-{ext}.json, tokenizer-{ext}.json and model-{ext}-q80.gguf (monolingual.rs:198-203): the GGUF
+        # file is recognised by its magic and dequantised at load (csrc/host/loader.h)
         import os
 
         lib = ffi.load_library()

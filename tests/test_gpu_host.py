@@ -289,3 +289,34 @@ def test_model_from_files_multilingual_and_errors(lib, tmp_path):
     with pytest.raises(ffi.Nb200Error) as e:
         d.blocking_try_to_model_from_files(*odd, compute="f32")
     assert e.value.status == 5 and "Unexpected number of mel bins" in str(e.value)
+
+
+def test_quantized_gguf_checkpoint_equals_its_dequantised_weights(lib, tmp_path):
+    """`ModelType::QuantizedTinyEn` (config-tiny-en.json, tokenizer-tiny-en.json, model-tiny-en-q80.gguf, monolingual.rs:198-203): the GGUF
+    file is dequantised at load, so the model must behave exactly like one built from the dequantised tensors."""
+    import json
+    import os
+
+    c, st, w, plan = planted("tiny.en")
+    d0 = str(tmp_path / "q")
+    os.makedirs(d0)
+    gg = os.path.join(d0, "model-tiny-en-q80.gguf")
+    deq = synth.write_gguf(gg, w)
+    assert any(np.abs(deq[k] - w[k].numpy()).max() > 0 for k in deq)  # the quantisation really changed the weights
+    cj, tj = os.path.join(d0, "config-tiny-en.json"), os.path.join(d0, "tokenizer-tiny-en.json")
+    with open(cj, "w") as f:
+        json.dump(c, f)
+    with open(tj, "w", encoding="utf-8") as f:
+        f.write(synth.synth_tokenizer_json(c["vocab_size"]))
+    dq = whisper.Definition.new(whisper.ModelType.QuantizedTinyEn, whisper.SelectedDevice.Cuda(0))
+    a = dq.blocking_try_to_model_from_files(cj, tj, gg, compute="f32")
+    b = whisper.Definition.new(whisper.ModelType.TinyEn, whisper.SelectedDevice.Cuda(0)).blocking_try_to_model(
+        {k: torch.from_numpy(v) for k, v in deq.items()}, compute="f32")
+    pcm = synth.synth_pcm("gauss", 3, 480_000)
+    ga, gb = a.transcribe(pcm.copy(), True), b.transcribe(pcm.copy(), True)
+    assert ga[1] == gb[1] and len(ga[1]) >= 1
+    fa, fb = a.ctx.fetch_features(0), b.ctx.fetch_features(0)
+    assert np.array_equal(fa, fb)
+    a.close()
+    b.close()
+    b.ctx.close()

@@ -262,3 +262,59 @@ def test_write_checkpoint_produces_the_three_hub_files(lib, tmp_path):
     assert t.special_tokens("<|en|>") == synth.special_tokens(c["vocab_size"])
     assert np.array_equal(ffi.safetensors_read(sf, "model.decoder.embed_tokens.weight"), w["model.decoder.embed_tokens.weight"].numpy())
     assert ffi.safetensors_read(sf, "model.encoder.embed_positions.weight").shape == (1500, c["d_model"])
+
+
+# ---- GGUF (q8_0 `Quantized*` checkpoints) ------------------------------------------------------------------------------------
+def test_gguf_q8_0_dequantises_exactly(lib, tmp_path):
+    c = synth.model_config("test-micro")
+    w = synth.synth_weights(c, seed=2, decoder=False)
+    w["extra.f16"] = torch.randn(4, 64).half()
+    p = str(tmp_path / "m.gguf")
+    deq = synth.write_gguf(p, {k: v for k, v in w.items() if k != "extra.f16"})
+    for k in list(deq)[:12]:
+        got, typ = ffi.gguf_read(p, k)
+        assert got.shape == tuple(w[k].shape)
+        assert typ == (8 if (w[k].ndim >= 2 and w[k].shape[-1] % 32 == 0) else 0)
+        assert np.array_equal(got, deq[k]), k                          # d (f16) * q (int8), exactly
+        if typ == 8:
+            amax = np.abs(w[k].numpy()).reshape(-1, 32).max(1)
+            assert np.all(np.abs(got - w[k].numpy()).reshape(-1, 32).max(1) <= amax / 127 * 0.51 + amax * 1e-3)  # half a step + f16 scale rounding
+    with pytest.raises(ffi.Nb200Error) as e:
+        ffi.gguf_read(p, "absent")
+    assert e.value.status == 9
+
+
+def test_gguf_v2_and_alignment(lib, tmp_path):
+    t = {"model.a.weight": np.arange(64, dtype=np.float32).reshape(2, 32) / 7, "model.b": np.arange(5, dtype=np.float32)}
+    for version, align in ((2, 32), (3, 64)):
+        p = str(tmp_path / f"v{version}.gguf")
+        deq = synth.write_gguf(p, t, version=version, alignment=align)
+        for k in t:
+            assert np.array_equal(ffi.gguf_read(p, k)[0], deq[k])
+
+
+@pytest.mark.parametrize("case", ["magic", "version", "truncated", "type", "row", "short"])
+def test_gguf_malformed_files_are_parse_errors(lib, tmp_path, case):
+    p = str(tmp_path / "bad.gguf")
+    synth.write_gguf(p, {"t": np.ones((2, 32), np.float32)})
+    raw = bytearray(open(p, "rb").read())
+    if case == "magic":
+        raw[0:4] = b"GGML"
+    elif case == "version":
+        raw[4:8] = struct.pack("<I", 1)
+    elif case == "truncated":
+        raw = raw[:-40]
+    elif case == "type":
+        i = raw.index(b"\x01\x00\x00\x00\x00\x00\x00\x00t")  # the tensor-info record of "t"
+        j = i + 9 + 4 + 16                                      # name, rank, two dims
+        raw[j:j + 4] = struct.pack("<I", 2)                     # Q4_0: not read
+    elif case == "row":
+        i = raw.index(b"\x01\x00\x00\x00\x00\x00\x00\x00t")
+        j = i + 9 + 4
+        raw[j:j + 8] = struct.pack("<Q", 31)                    # innermost dimension no longer a multiple of 32
+    elif case == "short":
+        raw = raw[:10]
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(ffi.Nb200Error) as e:
+        ffi.gguf_read(p, "t")
+    assert e.value.status == 8
