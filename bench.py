@@ -259,9 +259,14 @@ def main():
     gemm_ms = prof["gemm"]["ms"]
     gemm_launches = max(prof["gemm"]["launches"], 1)
     achieved_tf = gflops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM bytes per GEMM launch from ONE `ncu --set full` capture of a layer's four GEMMs (qkv 346 MB, out 436, fc1 444, fc2 850; profiles/
+    # r1e_gemm_full_summary.md) — only valid for the shape and batch it was captured on; the algorithmic bytes of the same four launches
+    # average 538 MB (operands + f32 residual in / out), so nothing is re-read from HBM
+    traffic = 5.19e8 if (args.model == "distil-large-v3" and B == 25 and args.compute == "bf16") else None
     roofline = {
         "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16, fused epilogue)" if args.compute == "bf16" else "sgemm_kernel (fp32 SIMT)",
-        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 GEMMs of a layer)",
+        "peak_source": peak_src,
         "flops_per_launch": gflops / gemm_launches, "avg_launch_ms": gemm_ms / gemm_launches, "launches": gemm_launches,
         "profiled_ms_per_step": ms_prof / args.steps,
         "share_of_step": {k: (v["ms"] / ms_prof if ms_prof > 0 else 0.0) for k, v in prof.items() if v["ms"] > 0},
