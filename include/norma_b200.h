@@ -159,6 +159,12 @@ NB200_API int nb200_reset_kv_cache(nb200_ctx *ctx);
 NB200_API int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
                         double *avg_logprob, double *no_speech_prob);
 
+/* how the greedy steady state runs: NB200_DECODE_AUTO (default) = the fused cooperative step kernel when the context supports it (bf16),
+ * NB200_DECODE_SEPARATE = the per-operation kernels replayed as a CUDA graph (always used for t > 0 and in F32 mode).  Same results up to the
+ * rounding of the GEMV inputs (the fused kernel feeds its tensor-core GEMVs bf16 activations). */
+typedef enum { NB200_DECODE_AUTO = 0, NB200_DECODE_SEPARATE = 1 } nb200_decode_mode;
+NB200_API int nb200_set_decode_mode(nb200_ctx *ctx, nb200_decode_mode mode);
+
 /* the same loop at any temperature: t = 0 is nb200_decode_greedy; t > 0 replaces `softmax(p / t)` + `WeightedIndex::sample`
  * (model.rs:340-348) by an inverse-CDF draw on the device from a counter-based generator seeded with `seed` (the reference
  * seeds StdRng from entropy, monolingual.rs:439, so only the distribution is comparable). */

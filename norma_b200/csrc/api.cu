@@ -891,6 +891,13 @@ int nb200_reset_kv_cache(nb200_ctx *ctx) {
     return NB200_OK;
 }
 
+int nb200_set_decode_mode(nb200_ctx *ctx, nb200_decode_mode mode) {
+    NB_TRY(check_ready(ctx, false, false));
+    if (mode != NB200_DECODE_AUTO && mode != NB200_DECODE_SEPARATE) return nb200_fail(ctx, NB200_INVALID_ARG, "set_decode_mode: %d", (int)mode);
+    ctx->decode_separate = mode == NB200_DECODE_SEPARATE;
+    return NB200_OK;
+}
+
 int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens, double *avg_logprob,
                         double *no_speech_prob) {
     return nb200_decode(ctx, n_windows, 0.0f, 0, max_new_tokens, tokens_out, n_tokens, avg_logprob, no_speech_prob);
@@ -922,7 +929,7 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     // greedy steady state: POLL steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 falls back to the
     // ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose sampler is a single-block kernel)
     static const bool fused_ok = [] { const char *e = getenv("NB200_DECODE_FUSED"); return !(e && e[0] == '0'); }();
-    bool use_fused = greedy && fused_ok && !ctx->fused_failed && decoder_fused_supported(ctx);
+    bool use_fused = greedy && fused_ok && !ctx->decode_separate && !ctx->fused_failed && decoder_fused_supported(ctx);
     const bool graph_ok = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto ensure_graph = [&]() -> int {

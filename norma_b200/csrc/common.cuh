@@ -143,6 +143,7 @@ struct nb200_ctx {
     float *d_fused_attn_ws = nullptr;  // split-K partials of the fused step's attention [max_batch][heads][64][66]
     void *d_fused_sync = nullptr;  // monotonic grid-barrier counter (u32, own 128 B line) | attention tickets [max_batch][heads]
     int fused_ctas = 0;            // cooperative grid of the fused decoder step (0 = not sized yet)
+    bool decode_separate = false;  // nb200_set_decode_mode(NB200_DECODE_SEPARATE)
     bool fused_failed = false;     // a cooperative launch was refused once: this context stays on the separate kernels
     void *d_lang = nullptr;      // detect_language scratch: [NB200_MAX_LANGS] u32 ids | [NB200_MAX_LANGS] f32 probs | i32 best
     void *d_sel_ws = nullptr;    // greedy select partials: [max_batch][32] float2 + [max_batch][32] SelCand

@@ -33,7 +33,7 @@ SYMBOLS = [
     "nb200_transcode_submit", "nb200_transcode_collect",
     "nb200_detect_language", "nb200_model_set_language_detection", "nb200_model_language", "nb200_model_script_push_language",
     "nb200_config_from_file", "nb200_mel_filters", "nb200_tokenizer_from_file", "nb200_tokenizer_destroy", "nb200_tokenizer_token_to_id",
-    "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read", "nb200_load_gguf", "nb200_gguf_read",
+    "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read", "nb200_load_gguf", "nb200_gguf_read", "nb200_set_decode_mode",
     "nb200_model_set_tokenizer", "nb200_model_from_files",
 ]
 
@@ -129,6 +129,7 @@ def load_library() -> C.CDLL:
         "nb200_tokenizer_language_tokens": ([p, u32p], i),
         "nb200_load_safetensors": ([p, C.c_char_p, C.POINTER(sz)], i),
         "nb200_safetensors_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i)], i),
+        "nb200_set_decode_mode": ([p, i], i),
         "nb200_load_gguf": ([p, C.c_char_p, C.POINTER(sz)], i),
         "nb200_gguf_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i), C.POINTER(i)], i),
         "nb200_model_set_tokenizer": ([p, p], i),
@@ -460,6 +461,10 @@ class Context:
         tok = C.c_uint32()
         self._ck(self.lib.nb200_detect_language(self.h, window, t.ctypes.data_as(C.POINTER(C.c_uint32)), t.size, C.byref(tok), _f32p(probs)))
         return tok.value, probs
+
+    def set_decode_mode(self, separate: bool):
+        """False: fused cooperative step kernel when supported (default); True: per-operation kernels replayed as a CUDA graph."""
+        self._ck(self.lib.nb200_set_decode_mode(self.h, int(bool(separate))))
 
     def decode(self, n_windows: int = 1, temperature: float = 0.0, seed: int = 0, max_new_tokens: int = 0):
         toks = np.zeros((n_windows, self.P), np.uint32)

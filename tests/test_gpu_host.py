@@ -320,3 +320,45 @@ def test_quantized_gguf_checkpoint_equals_its_dequantised_weights(lib, tmp_path)
     a.close()
     b.close()
     b.ctx.close()
+
+
+def test_fused_and_separate_decode_agree(lib):
+    """The fused cooperative step kernel against the per-operation kernels (nb200_set_decode_mode) on three windows in lock-step:
+    a planted, confident decoder gives identical tokens; a random-init decoder run to the stop rule (max_target_positions - 1: 28 launches
+    of 16 positions) must stop at the same length with the same structure, and agree token for token in F32-free bf16 only up to rounding,
+    so the comparison there is on everything the reference's rules force (prompt, first timestamp window, final eot, length)."""
+    c, st, w, plan = planted("tiny.en")
+    ctx = ffi.Context(c, compute="bf16", max_batch=3)
+    ctx.set_mel_filters(filters.mel_filters(80))
+    ctx.load_weights(w)
+    ctx.set_tokens(st.sot, st.eot, st.task, st.lang, st.no_speech, st.no_timestamps, st.ts_zero, st.ts_one)
+    pcm = np.stack([synth.synth_pcm("gauss", 0), synth.synth_pcm("uniform", 1), synth.synth_pcm("bursts", 2)])
+    ctx.transcode_batch(pcm, want_output=False)
+    want = [st.sot, st.lang, st.task] + [plan[p] for p in range(2, 9)]
+    fused = ctx.decode(3, 0.0)
+    ctx.set_decode_mode(True)
+    separate = ctx.decode(3, 0.0)
+    ctx.set_decode_mode(False)
+    for b in range(3):
+        assert fused[b]["tokens"] == want == separate[b]["tokens"]
+        assert abs(fused[b]["avg_logprob"] - separate[b]["avg_logprob"]) < 5e-3
+        assert abs(fused[b]["no_speech_prob"] - separate[b]["no_speech_prob"]) < 1e-6  # prompt positions run on the same kernels
+    ctx.close()
+    # random-init decoder, run to the reference's stop rule
+    c = synth.model_config("test-micro")
+    ctx = ffi.Context(c, compute="bf16", max_batch=2)
+    ctx.set_mel_filters(filters.mel_filters(80))
+    ctx.load_weights(synth.synth_weights(c, seed=1))
+    tok = synth.special_tokens(c["vocab_size"])
+    ctx.set_tokens(**tok)
+    ctx.transcode_batch(np.stack([synth.synth_pcm("gauss", 0), synth.synth_pcm("uniform", 1)]), want_output=False)
+    a = ctx.decode(2, 0.0)
+    ctx.set_decode_mode(True)
+    b2 = ctx.decode(2, 0.0)
+    for x, y in zip(a, b2):
+        assert x["tokens"][:3] == y["tokens"][:3] == [tok["sot"], tok["lang"], tok["task"]]
+        assert x["tokens"][-1] == tok["eot"] == y["tokens"][-1]
+        assert len(x["tokens"]) <= c["max_target_positions"] and len(y["tokens"]) <= c["max_target_positions"]
+        n_same = next((i for i, (p, q) in enumerate(zip(x["tokens"], y["tokens"])) if p != q), min(len(x["tokens"]), len(y["tokens"])))
+        assert n_same >= 4  # prompt + the first sampled token (chosen by the same select kernel from the same logits)
+    ctx.close()
