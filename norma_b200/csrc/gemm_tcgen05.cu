@@ -485,13 +485,19 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     static int mode = -1, epi = -1;  // NB200_GEMM=1cta: single-CTA kernel; NB200_EPI=direct: thread-per-row stores (A/B comparison)
     if (mode < 0) {
         const char *ev = getenv("NB200_GEMM");
-        mode = (ev && !strcmp(ev, "1cta")) ? 1 : 2;
+        mode = (ev && !strcmp(ev, "1cta")) ? 1 : (ev && !strcmp(ev, "1cta128")) ? 3 : 2;
         ev = getenv("NB200_EPI");
         epi = (ev && !strcmp(ev, "direct")) ? 0 : 1;
     }
-    const bool pair = mode == 2 && s.N >= 256;
-    // single-CTA: BN = 256 unless N is small enough that 128-wide tiles give a better wave fit
-    const bool use128 = !pair && ((s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
+    // Tile configuration: the CTA-pair 256 x 256 tile wins everywhere except for ONE window's worth of rows (streaming, BASELINE configs 4 / 5 at
+    // B = 1) on the N = d_model GEMMs, where 6 x 5 pair tiles occupy 30 of 74 pairs; 128 x 128 single-CTA tiles (120 of 148 CTAs) are then
+    // faster (scripts/gpu_gemm_fit.py, M = 1500: out-proj 18.6 -> 14.4 us, fc2 36.5 -> 28.5 us; from M = 3000 on the pair tile is as fast or faster)
+    bool pair = mode == 2 && s.N >= 256;
+    bool use128 = !pair && (mode == 3 || (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
+    if (mode == 2 && (long long)s.rows_per_batch * s.batch <= 2048 && s.N <= 1536 && s.N % 128 == 0 && getenv("NB200_GEMM_NOFIT") == nullptr) {
+        pair = false;
+        use128 = true;
+    }
     const int BN = use128 ? 128 : 256;
     const int tile_m = pair ? 256 : BM;
     GemmTcParams p;
