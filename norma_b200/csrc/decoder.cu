@@ -1090,33 +1090,51 @@ __device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 
             m = sd; l = 1.f; a0 = vr.x; a1 = vr.y;
             k1 = jn;  // the loop below covers the cached keys only
         }
-        // two keys per iteration; the next pair's K / V rows are requested before this pair's softmax chain (L2 latency ~ the chain)
-        __nv_bfloat162 kA, vA, kB, vB;
-        auto load_pair = [&](int jj) {
-            const int j2 = jj + 1 < k1 ? jj + 1 : jj;
-            kA = *(const __nv_bfloat162 *)(cb + (size_t)jj * 2 * d);
-            vA = *(const __nv_bfloat162 *)(cb + (size_t)jj * 2 * d + d);
-            kB = *(const __nv_bfloat162 *)(cb + (size_t)j2 * 2 * d);
-            vB = *(const __nv_bfloat162 *)(cb + (size_t)j2 * 2 * d + d);
+        // four keys per iteration (their dot products reduce through the same five shuffle rounds, then ONE online-softmax update), the next
+        // four K / V rows requested before this group's softmax chain: the loop is a chain of L2 round trips and shuffle latencies, not of work
+        __nv_bfloat162 kr[4], vr[4];
+        auto load4 = [&](int jj) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int jt = jj + t < k1 ? jj + t : k1 - 1;  // past the end: re-read the last row (its score is masked below)
+                kr[t] = *(const __nv_bfloat162 *)(cb + (size_t)jt * 2 * d);
+                vr[t] = *(const __nv_bfloat162 *)(cb + (size_t)jt * 2 * d + d);
+            }
         };
-        if (j < k1) load_pair(j);
+        if (j < k1) load4(j);
 #pragma unroll 1
-        for (; j < k1; j += 2) {
-            const bool two = j + 1 < k1;
-            const float2 kAf = __bfloat1622float2(kA), kBf = __bfloat1622float2(kB), vAf = __bfloat1622float2(vA), vBf = __bfloat1622float2(vB);
-            if (j + 2 < k1) load_pair(j + 2);
-            float sA = qv.x * kAf.x + qv.y * kAf.y, sB = qv.x * kBf.x + qv.y * kBf.y;
+        for (; j < k1; j += 4) {
+            float sc[4];
+            float2 vf[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 kf = __bfloat1622float2(kr[t]);
+                vf[t] = __bfloat1622float2(vr[t]);
+                sc[t] = qv.x * kf.x + qv.y * kf.y;
+            }
+            const int left = k1 - j;
+            if (j + 4 < k1) load4(j + 4);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                sA += __shfl_xor_sync(0xffffffffu, sA, o);
-                sB += __shfl_xor_sync(0xffffffffu, sB, o);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) sc[t] += __shfl_xor_sync(0xffffffffu, sc[t], o);
             }
-            if (!two) sB = -INFINITY;
-            const float mn = fmaxf(m, fmaxf(sA, sB));
-            const float al = expf(m - mn), pA = expf(sA - mn), pB = expf(sB - mn);  // m = -inf on the first pair: al = 0
-            l = l * al + pA + pB;
-            a0 = a0 * al + pA * vAf.x + pB * vBf.x;
-            a1 = a1 * al + pA * vAf.y + pB * vBf.y;
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+                if (t >= left) sc[t] = -INFINITY;
+            const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));
+            const float al = __expf(m - mn);  // m = -inf on the first group: 0
+            float ps = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float pt = __expf(sc[t] - mn);
+                ps += pt;
+                o0 = fmaf(pt, vf[t].x, o0);
+                o1 = fmaf(pt, vf[t].y, o1);
+            }
+            l = l * al + ps;
+            a0 = a0 * al + o0;
+            a1 = a1 * al + o1;
             m = mn;
         }
         float *wsb = ws + ((size_t)b * H + h) * S * ATT_WS;
