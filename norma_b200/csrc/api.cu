@@ -111,19 +111,19 @@ int need(nb200_ctx *ctx, const std::string &name, size_t numel, const HostTensor
 }
 
 int up_vec(nb200_ctx *ctx, const std::string &name, size_t n, float **out) {
-    const HostTensor *t;
+    const HostTensor *t = nullptr;
     NB_TRY(need(ctx, name, n, &t));
     return upload_f32(ctx, t->data, out);
 }
 int up_mat(nb200_ctx *ctx, const std::string &name, size_t n, void **out) {
-    const HostTensor *t;
+    const HostTensor *t = nullptr;
     NB_TRY(need(ctx, name, n, &t));
     return upload_compute(ctx, t->data, out);
 }
 
 // concatenated [q | k | v] weight and bias ([3d][d], [3d] with zeros for the bias-less k_proj)
 int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b) {
-    const HostTensor *q, *k, *v, *bq, *bv;
+    const HostTensor *q = nullptr, *k = nullptr, *v = nullptr, *bq = nullptr, *bv = nullptr;
     NB_TRY(need(ctx, p + "q_proj.weight", (size_t)d * d, &q));
     NB_TRY(need(ctx, p + "k_proj.weight", (size_t)d * d, &k));
     NB_TRY(need(ctx, p + "v_proj.weight", (size_t)d * d, &v));
@@ -141,7 +141,7 @@ int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b) {
 
 // conv weight [co][ci][3] -> [co][k*ci_n + ci] (tap-major) so a GEMM row is 3 consecutive time-major input rows
 int up_conv(nb200_ctx *ctx, const std::string &name, int co, int ci, void **out) {
-    const HostTensor *t;
+    const HostTensor *t = nullptr;
     NB_TRY(need(ctx, name, (size_t)co * ci * 3, &t));
     std::vector<float> W((size_t)co * ci * 3);
     for (int o = 0; o < co; ++o)

@@ -58,7 +58,9 @@ __device__ __forceinline__ void pin16(const uint32_t *r) {
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tSj, uint32_t tO, uint32_t s_full, uint32_t s_par, uint32_t p_full, uint32_t o_done, uint32_t o_par_prev,
                                               int lane, bool first, int valid, float &m, float &l, long long *tm = nullptr) {
+#ifdef NB200_ATTN_TIMING
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+#endif
     AT_CLK(c0);
     ptx::mbar_wait(s_full, s_par);
     ptx::tc_fence_after();

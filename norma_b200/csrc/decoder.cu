@@ -1199,8 +1199,9 @@ decoder_step_fused_kernel(const FusedArgs a) {
         if (tid == FS_CTHREADS) fs_produce(a, sbase, full0, empty0, &go_step);
         return;
     }
+#ifdef NB200_DECODE_TIMING
     int stamp_i = 0;
-    (void)stamp_i;
+#endif
     const int d = a.d, B = a.B, V = a.V, P = a.P, T = a.T, H = a.H;
     const int nch = gridDim.x;  // vocabulary chunks per window in the select: one per CTA
     unsigned cnt = 0, target = __ldcg(a.sync_epoch);
@@ -1216,7 +1217,9 @@ decoder_step_fused_kernel(const FusedArgs a) {
         break;
     }
     if (tid == 0) go_step = step + 1;
+#ifdef NB200_DECODE_TIMING
     stamp_i = 0;
+#endif
     DEC_STAMP();
     for (int l = 0; l < a.L; ++l) {
         const DecLayer w = a.layers[l];
