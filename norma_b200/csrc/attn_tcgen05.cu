@@ -43,12 +43,14 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+#ifdef NB200_ATTN_TIMING
 // Empty asm that consumes 16 registers: everything they depend on is computed before the next asm volatile as far as nvcc is
 // concerned (ptxas may still sink it).  Only the timing build uses it, to keep the clock64 brackets honest.
 __device__ __forceinline__ void pin16(const uint32_t *r) {
     asm volatile("" ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
                  "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
 }
+#endif
 
 #ifdef NB200_ATTN_TIMING
 #define AT_CLK(x) x = clock64()
