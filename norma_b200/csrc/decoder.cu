@@ -982,7 +982,7 @@ __device__ __noinline__ void fs_stage(const FusedArgs &a, const float *__restric
 // one of FS_MMA_WARPS warps; the first version did this with FFMA on 16 warps and spent ~300 issue slots per weight row, more than
 // the 0.9 us a 40 KB tile takes to arrive from HBM.
 __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, int ldx, const float *ln_g, const float *ln_b, float *ln_out, bool from_tokens,
-                                     int pos, SkinnyEpi e, uint8_t *smem, uint32_t full0, uint32_t empty0, unsigned &cnt, float *stats) {
+                                     int pos, SkinnyEpi e, uint8_t *smem, uint32_t full0, uint32_t empty0, unsigned &cnt, float *stats, float *kpart) {
     const FsJob job = fs_job(a, j);
     const int K = job.K, N = job.N, KC = a.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -995,6 +995,71 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
         const int Bd = min(cap, a.B - m0);
         fs_stage(a, x ? x + (size_t)m0 * ldx : nullptr, ldx, K, m0, Bd, ln_g, ln_b, ln_out ? ln_out + (size_t)m0 * K : nullptr, from_tokens, pos, xs, stats);
         int gi = 0;
+        if (n_chunks == FS_MMA_WARPS) {
+            // K = 4 d_model (fc2): a group's four K chunks are four consecutive ring tiles; MMA warp w takes chunk w of EVERY group, so the four
+            // tiles are consumed concurrently instead of one after the other, and warp 0 folds the four partial fragments through `kpart`
+#pragma unroll 1
+            for (int t = blockIdx.x; t < n_groups; t += gridDim.x, ++gi, cnt += n_chunks) {
+                if (warp >= FS_MMA_WARPS) continue;
+                float acc[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+                float ebias[2] = {0.f, 0.f}, eres[4] = {0.f, 0.f, 0.f, 0.f};
+                if (warp == 0) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int n = t * 16 + (lane >> 2) + (r >> 1) * 8, m = (lane & 3) * 2 + (r & 1);
+                        if (n < N && m < Bd) {
+                            if (e.bias && (r & 1) == 0) ebias[r >> 1] = e.bias[n];
+                            if (e.residual) eres[r] = __ldcg(e.residual + (size_t)(m0 + m) * e.ldr + n);
+                        }
+                    }
+                }
+                const int bn = lane >> 2;
+                const bf16 *xk = xs + (bn < Bd ? bn : 0) * K + (lane & 3) * 2 + warp * KC;
+                const unsigned ct = cnt + warp, st = ct % FS_STAGES;
+                ptx::mbar_wait(full0 + 8 * st, (ct / FS_STAGES) & 1);
+                const uint32_t arow = ring + st * FS_TILE_BYTES + (lane & 15) * pitch + (lane >> 4) * 16;
+#pragma unroll 4
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                    uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
+                    if (bn < Bd) {
+                        b0 = *(const uint32_t *)(xk + ks * 16);
+                        b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+                    }
+                    float *dd = acc[ks & 3];
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                 : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(empty0 + 8 * st);
+                float4 *kp = (float4 *)kpart + (gi & 1) * 3 * 32;  // double-buffered by group parity
+                const float4 mine = make_float4(acc[0][0] + acc[1][0] + acc[2][0] + acc[3][0], acc[0][1] + acc[1][1] + acc[2][1] + acc[3][1],
+                                                acc[0][2] + acc[1][2] + acc[2][2] + acc[3][2], acc[0][3] + acc[1][3] + acc[2][3] + acc[3][3]);
+                if (warp > 0) kp[(warp - 1) * 32 + lane] = mine;
+                asm volatile("bar.sync 6, 128;" ::: "memory");  // the four MMA warps
+                if (warp == 0) {
+                    const float4 p1 = kp[lane], p2 = kp[32 + lane], p3 = kp[64 + lane];
+                    const float vv[4] = {mine.x + p1.x + p2.x + p3.x, mine.y + p1.y + p2.y + p3.y, mine.z + p1.z + p2.z + p3.z, mine.w + p1.w + p2.w + p3.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int n = t * 16 + (lane >> 2) + (r >> 1) * 8, m = (lane & 3) * 2 + (r & 1);
+                        if (n < N && m < Bd) {
+                            float v = vv[r] + ebias[r >> 1];
+                            if (n < e.n_scale) v *= e.scale;
+                            if (e.act) v = gelu_tanh_precise(v);
+                            v += eres[r];
+                            e.out[(size_t)(m0 + m) * e.ldo + n] = v;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll 1
         for (int t = blockIdx.x; t < n_groups; t += gridDim.x, ++gi) {
             if (warp != (gi % FS_MMA_WARPS)) {  // not this warp's group (warps >= FS_MMA_WARPS own none): just keep the tile count
@@ -1182,6 +1247,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
     __shared__ float red[32];
     __shared__ int red_i[32];
     __shared__ float ln_stats[32];
+    __shared__ __align__(16) float kpart[2 * 3 * 32 * 4];  // K-split partial fragments of fc2 (fs_gemv)
     __shared__ volatile int go_step;
     const int tid = threadIdx.x;
     const uint32_t sbase = ptx::smem_u32(smem);
@@ -1227,7 +1293,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
         bf16 *ckv = a.cross_kv + (size_t)l * a.max_batch * T * 2 * d;
         SkinnyEpi e{};
         e.bias = w.bqkv; e.out = a.dqkv; e.ldo = 3 * d; e.scale = a.qscale; e.n_scale = 2 * d;
-        fs_gemv(a, 6 * l + 0, l == 0 ? nullptr : a.dx, d, w.ln1g, w.ln1b, nullptr, l == 0, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 0, l == 0 ? nullptr : a.dx, d, w.ln1g, w.ln1b, nullptr, l == 0, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         fs_attn(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, d);
@@ -1235,12 +1301,12 @@ decoder_step_fused_kernel(const FusedArgs a) {
         DEC_STAMP();
         e = SkinnyEpi{};
         e.bias = w.bo; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
-        fs_gemv(a, 6 * l + 1, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 1, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
         e.bias = w.cbq; e.out = a.dq; e.ldo = d; e.scale = a.qscale; e.n_scale = d;
-        fs_gemv(a, 6 * l + 2, a.dx, d, w.lncg, w.lncb, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 2, a.dx, d, w.lncg, w.lncb, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         fs_attn(a.dq, d, ckv, T, d, H, B, T, false, nullptr, 0, 0, 0, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn, d);
@@ -1248,24 +1314,24 @@ decoder_step_fused_kernel(const FusedArgs a) {
         DEC_STAMP();
         e = SkinnyEpi{};
         e.bias = w.cbo; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
-        fs_gemv(a, 6 * l + 3, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 3, a.dattn, d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
         e.bias = w.b1; e.out = a.dff; e.ldo = 4 * d; e.act = 1;
-        fs_gemv(a, 6 * l + 4, a.dx, d, w.ln2g, w.ln2b, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 4, a.dx, d, w.ln2g, w.ln2b, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
         e.bias = w.b2; e.out = a.dx; e.ldo = d; e.residual = a.dx; e.ldr = d;
-        fs_gemv(a, 6 * l + 5, a.dff, 4 * d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * l + 5, a.dff, 4 * d, nullptr, nullptr, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
     }
     {   // final LayerNorm fused into the tied-embedding logits; CTA 0 leaves the hidden state in dhid
         SkinnyEpi e{};
         e.out = a.logits; e.ldo = V;
-        fs_gemv(a, 6 * a.L, a.dx, d, a.lndec_g, a.lndec_b, a.dhid, false, pos, e, smem, full0, empty0, cnt, ln_stats);
+        fs_gemv(a, 6 * a.L, a.dx, d, a.lndec_g, a.lndec_b, a.dhid, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
     }
     grid_sync(a.sync_counter, target);
     DEC_STAMP();
