@@ -1122,6 +1122,105 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
     }
 }
 
+// Self attention of the fused step when there are no more (window, head) pairs than CTAs (B <= 7 at 20 heads): one pair per CTA, its
+// (at most 448) keys split over the 16 consumer warps, the partial (m, l, o[64]) folded through shared memory — no global workspace,
+// fences or tickets as in the split-K version below (6.9 -> 4.8 us at B = 1).  Eight lanes share a key (16 bytes of K and of
+// V per lane), so a warp advances four keys per iteration; the next iteration's rows are requested before this one's softmax update.
+__device__ __forceinline__ void osm_merge_fast(float &m, float &l, float *acc, float m2, float l2, const float *acc2) {
+    const float mn = fmaxf(m, m2);
+    const float a = (m == -INFINITY) ? 0.f : __expf(m - mn), b = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+    l = l * a + l2 * b;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = acc[t] * a + acc2[t] * b;
+    m = mn;
+}
+
+__device__ __noinline__ void fs_attn_cta(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int H, int B, int n_keys, bool append,
+                                         const float *__restrict__ newkv, int ldkv, int koff, int voff, float *__restrict__ out, int ldo, float *sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l8 = lane & 7, grp = lane >> 3;
+    const unsigned gmask = 0xffu << (grp * 8);
+#pragma unroll 1
+    for (int it = blockIdx.x; it < B * H; it += gridDim.x) {
+        const int h = it % H, b = it / H;
+        bf16 *cb = cache + (size_t)b * Tmax * 2 * d + h * HEAD_DIM + l8 * 8;
+        float qr[8];
+        {
+            const float *qp = q + (size_t)b * ldq + h * HEAD_DIM + l8 * 8;
+            const float4 qa = __ldcg((const float4 *)qp), qc = __ldcg((const float4 *)qp + 1);
+            qr[0] = qa.x; qr[1] = qa.y; qr[2] = qa.z; qr[3] = qa.w; qr[4] = qc.x; qr[5] = qc.y; qr[6] = qc.z; qr[7] = qc.w;
+        }
+        const int chunk = (n_keys + FS_WARPS - 1) / FS_WARPS, k0 = warp * chunk, k1 = min(n_keys, k0 + chunk);
+        float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+        uint4 kn = make_uint4(0u, 0u, 0u, 0u), vn = kn;
+        auto fetch = [&](int jj) {  // K / V row jj for this lane; the position being decoded comes from the QKV GEMV and joins the cache
+            if (append && jj == n_keys - 1) {
+                const float *kp = newkv + (size_t)b * ldkv + koff + h * HEAD_DIM + l8 * 8, *vp = newkv + (size_t)b * ldkv + voff + h * HEAD_DIM + l8 * 8;
+                const float4 k0f = __ldcg((const float4 *)kp), k1f = __ldcg((const float4 *)kp + 1), v0f = __ldcg((const float4 *)vp), v1f = __ldcg((const float4 *)vp + 1);
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(k0f.x, k0f.y), t1 = __floats2bfloat162_rn(k0f.z, k0f.w), t2 = __floats2bfloat162_rn(k1f.x, k1f.y),
+                               t3 = __floats2bfloat162_rn(k1f.z, k1f.w);
+                kn = make_uint4(*(uint32_t *)&t0, *(uint32_t *)&t1, *(uint32_t *)&t2, *(uint32_t *)&t3);
+                t0 = __floats2bfloat162_rn(v0f.x, v0f.y); t1 = __floats2bfloat162_rn(v0f.z, v0f.w); t2 = __floats2bfloat162_rn(v1f.x, v1f.y);
+                t3 = __floats2bfloat162_rn(v1f.z, v1f.w);
+                vn = make_uint4(*(uint32_t *)&t0, *(uint32_t *)&t1, *(uint32_t *)&t2, *(uint32_t *)&t3);
+                *(uint4 *)(cb + (size_t)jj * 2 * d) = kn;
+                *(uint4 *)(cb + (size_t)jj * 2 * d + d) = vn;
+            } else {
+                kn = *(const uint4 *)(cb + (size_t)jj * 2 * d);
+                vn = *(const uint4 *)(cb + (size_t)jj * 2 * d + d);
+            }
+        };
+        int j = k0 + grp;
+        if (j < k1) fetch(j);
+#pragma unroll 1
+        for (; j < k1; j += 4) {
+            const uint4 ku = kn, vu = vn;
+            if (j + 4 < k1) fetch(j + 4);
+            const float2 kf0 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.x), kf1 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.y);
+            const float2 kf2 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.z), kf3 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.w);
+            float sd = qr[0] * kf0.x + qr[1] * kf0.y + qr[2] * kf1.x + qr[3] * kf1.y + qr[4] * kf2.x + qr[5] * kf2.y + qr[6] * kf3.x + qr[7] * kf3.y;
+            sd += __shfl_xor_sync(gmask, sd, 1);  // group-local mask: the four groups of a warp run different trip counts
+            sd += __shfl_xor_sync(gmask, sd, 2);
+            sd += __shfl_xor_sync(gmask, sd, 4);
+            const float mn = fmaxf(m, sd);
+            const float al = __expf(m - mn), pw = __expf(sd - mn);  // m = -inf on the first key: al = 0
+            const float2 vf0 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.x), vf1 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.y);
+            const float2 vf2 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.z), vf3 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.w);
+            l = l * al + pw;
+            acc[0] = acc[0] * al + pw * vf0.x; acc[1] = acc[1] * al + pw * vf0.y; acc[2] = acc[2] * al + pw * vf1.x; acc[3] = acc[3] * al + pw * vf1.y;
+            acc[4] = acc[4] * al + pw * vf2.x; acc[5] = acc[5] * al + pw * vf2.y; acc[6] = acc[6] * al + pw * vf3.x; acc[7] = acc[7] * al + pw * vf3.y;
+            m = mn;
+        }
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {  // the four key groups of the warp
+            float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o), a2[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a2[t] = __shfl_xor_sync(0xffffffffu, acc[t], o);
+            osm_merge_fast(m, l, acc, m2, l2, a2);
+        }
+        if (grp == 0) {
+            float *o = sm + (warp * 8 + l8) * 10;
+            o[0] = m; o[1] = l;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[2 + t] = acc[t];
+        }
+        cbar();
+        if (warp == 0 && grp == 0) {  // the 16 warps
+#pragma unroll 1
+            for (int w2 = 1; w2 < FS_WARPS; ++w2) {
+                const float *o = sm + (w2 * 8 + l8) * 10;
+                osm_merge_fast(m, l, acc, o[0], o[1], o + 2);
+            }
+            float *op = out + (size_t)b * ldo + h * HEAD_DIM + l8 * 8;
+            const float inv = 1.0f / l;
+            *(float4 *)op = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+            *((float4 *)op + 1) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+        }
+        cbar();  // sm is reused by the next pair
+    }
+}
+
 // Split-K single-query attention of the fused step: one (head, window, split) item per WARP.  A lane owns two of the 64 head
 // dimensions, so a K (or V) row is one coalesced 128-byte access; the warp walks the keys of its split two at a time with an online
 // softmax, writes (m, l, o[64]) to the workspace, and the warp that takes the last ticket of a (window, head) folds the S partials
@@ -1247,6 +1346,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
     __shared__ float red[32];
     __shared__ int red_i[32];
     __shared__ float ln_stats[32];
+    __shared__ float att_sm[FS_WARPS * 8 * 10];  // per-warp (m, l, o[8]) partials of fs_attn_cta
     __shared__ __align__(16) float kpart[2 * 3 * 32 * 4];  // K-split partial fragments of fc2 (fs_gemv)
     __shared__ volatile int go_step;
     const int tid = threadIdx.x;
@@ -1296,7 +1396,8 @@ decoder_step_fused_kernel(const FusedArgs a) {
         fs_gemv(a, 6 * l + 0, l == 0 ? nullptr : a.dx, d, w.ln1g, w.ln1b, nullptr, l == 0, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
-        fs_attn(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, d);
+        if (B * H <= (int)gridDim.x) fs_attn_cta(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.dattn, d, att_sm);
+        else fs_attn(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, d);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
@@ -1309,6 +1410,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
         fs_gemv(a, 6 * l + 2, a.dx, d, w.lncg, w.lncb, nullptr, false, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
+        // (1500 keys per pair are too many for one CTA's 16 loads in flight: 19.5 us against 14.6 us split over the grid)
         fs_attn(a.dq, d, ckv, T, d, H, B, T, false, nullptr, 0, 0, 0, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn, d);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
