@@ -929,7 +929,7 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
     // greedy steady state: POLL steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 falls back to the
     // ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose sampler is a single-block kernel)
     static const bool fused_ok = [] { const char *e = getenv("NB200_DECODE_FUSED"); return !(e && e[0] == '0'); }();
-    bool use_fused = greedy && fused_ok && !ctx->decode_separate && !ctx->fused_failed && decoder_fused_supported(ctx);
+    bool use_fused = greedy && fused_ok && !ctx->decode_separate && !ctx->fused_failed && decoder_fused_supported(ctx) && B <= decoder_fused_max_windows();
     const bool graph_ok = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
     cudaGraphExec_t gexec = nullptr;
     auto ensure_graph = [&]() -> int {

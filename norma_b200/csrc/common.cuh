@@ -235,6 +235,7 @@ int decoder_set_dyn(nb200_ctx *ctx, int pos, int max_new, float temperature, uns
 int decoder_nospeech(nb200_ctx *ctx, int n_windows);
 int decoder_step_fused(nb200_ctx *ctx, int n_windows, int n_steps);  // n_steps greedy steps in one cooperative launch (device-resident position)
 bool decoder_fused_supported(const nb200_ctx *ctx);
+int decoder_fused_max_windows();
 int decoder_fused_prepare(nb200_ctx *ctx);
 int decoder_fused_ws_floats(const nb200_ctx *ctx);  // one greedy step, one cooperative launch (device-resident position)
 constexpr int NB200_MAX_LANGS = 1024;

@@ -529,6 +529,44 @@ select_stats_kernel(const float *__restrict__ logits, int V, float2 *__restrict_
     select_stats_body(logits, V, ws_a, blockIdx.x, blockIdx.y, SEL_CH, red);
 }
 
+// which rule(s) of norma's token selection can apply to window b (mode 0 / 1 are known from the token state; otherwise both 2 and 3 are prepared)
+__device__ __forceinline__ void cand_modes(const SelectParams &sp, int b, int len, int last_ts, int &mode_a, int &mode_b) {
+    const int nts = (int)sp.nts;
+    mode_b = -1;
+    if (last_ts < 0) mode_a = 0;
+    else {
+        const uint32_t l_tok = __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 1);
+        const bool has_sl = len >= 2;
+        const uint32_t sl_tok = has_sl ? __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 2) : 0u;
+        if ((int)l_tok > nts) mode_a = (has_sl && sl_tok >= sp.eot) ? 1 : 2;
+        else { mode_a = 2; mode_b = 3; }
+    }
+}
+// one vocabulary entry (probability p, suppression mask sup) folded into a thread's share of sum_ts / max_text and its arg-max candidates
+__device__ __forceinline__ void cand_update(const SelectParams &sp, int mode_a, int mode_b, int last_ts, int i, float p, float sup, float &ts, float &mt,
+                                            float &ba, float &bb, int &ia, int &ib) {
+    const int nts = (int)sp.nts;
+    auto masked = [&](int mode) -> bool {
+        if (mode == 0) return i < (int)sp.ts_zero || i > (int)sp.ts_one;
+        bool mk = sup != 0.f;
+        if (mode == 1) mk |= i > nts;
+        else if (mode == 2) mk |= i <= nts || i <= last_ts;
+        else mk |= (i > nts && i <= last_ts);
+        return mk;
+    };
+    if (mode_b >= 0) {
+        const float ps = p + sup;
+        if (i > nts) ts += ps;
+        else if (i < nts) mt = fmaxf(mt, ps);
+    }
+    const float pa = masked(mode_a) ? -INFINITY : p;
+    if (pa >= ba) { ba = pa; ia = i; }
+    if (mode_b >= 0) {
+        const float pb = masked(mode_b) ? -INFINITY : p;
+        if (pb >= bb) { bb = pb; ib = i; }
+    }
+}
+
 // phase B: with the global (max, sum) every chunk yields its share of sum_ts / max_text and the arg-max candidates of the
 // rule(s) that can still apply: mode 0 / 1 are known from the token state; otherwise both 2 and 3 are prepared
 template <int BAR = 0, int NT = 0>
@@ -536,7 +574,7 @@ __device__ __forceinline__ void select_cand_body(const SelectParams &sp, const f
                                                  float *red, int *red_i) {
     const int tid = threadIdx.x, nt = NT ? NT : (int)blockDim.x;
     if (__ldcg(sp.done + b)) return;  // (state and logits change every step of a multi-step launch: read them from L2)
-    const int V = sp.V, nts = (int)sp.nts;
+    const int V = sp.V;
     // global (max, sum) from the chunk partials, folded by the whole block (one partial per thread: nch can be as large as the grid)
     float pm = -INFINITY;
 #pragma unroll 1
@@ -547,42 +585,14 @@ __device__ __forceinline__ void select_cand_body(const SelectParams &sp, const f
     for (int k = tid; k < nch; k += nt) ps += __ldcg(&ws_a[b * nch + k].y) * expf(__ldcg(&ws_a[b * nch + k].x) - M);
     const float S = block_sum<BAR, NT>(ps, red);
     const int len = __ldcg(sp.len + b), last_ts = __ldcg(sp.last_ts + b);
-    int mode_a, mode_b = -1;
-    if (last_ts < 0) mode_a = 0;
-    else {
-        const uint32_t l_tok = __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 1);
-        const bool has_sl = len >= 2;
-        const uint32_t sl_tok = has_sl ? __ldcg(sp.tokens + (size_t)b * sp.max_pos + len - 2) : 0u;
-        if ((int)l_tok > nts) mode_a = (has_sl && sl_tok >= sp.eot) ? 1 : 2;
-        else { mode_a = 2; mode_b = 3; }
-    }
+    int mode_a, mode_b;
+    cand_modes(sp, b, len, last_ts, mode_a, mode_b);
     const int per = (V + nch - 1) / nch, lo = c * per, hi = min(V, lo + per);
     const float *x = sp.logits + (size_t)b * V;
     float ts = 0.f, mt = -INFINITY, ba = -INFINITY, bb = -INFINITY;
     int ia = -1, ib = -1;
-    auto masked = [&](int mode, int i, float sup) -> bool {
-        if (mode == 0) return i < (int)sp.ts_zero || i > (int)sp.ts_one;
-        bool mk = sup != 0.f;
-        if (mode == 1) mk |= i > nts;
-        else if (mode == 2) mk |= i <= nts || i <= last_ts;
-        else mk |= (i > nts && i <= last_ts);
-        return mk;
-    };
 #pragma unroll 1
-    for (int i = lo + tid; i < hi; i += nt) {
-        const float p = expf(__ldcg(x + i) - M) / S, sup = sp.suppress[i];
-        if (mode_b >= 0) {
-            const float ps = p + sup;
-            if (i > nts) ts += ps;
-            else if (i < nts) mt = fmaxf(mt, ps);
-        }
-        const float pa = masked(mode_a, i, sup) ? -INFINITY : p;
-        if (pa >= ba) { ba = pa; ia = i; }
-        if (mode_b >= 0) {
-            const float pb = masked(mode_b, i, sup) ? -INFINITY : p;
-            if (pb >= bb) { bb = pb; ib = i; }
-        }
-    }
+    for (int i = lo + tid; i < hi; i += nt) cand_update(sp, mode_a, mode_b, last_ts, i, expf(__ldcg(x + i) - M) / S, sp.suppress[i], ts, mt, ba, bb, ia, ib);
     auto arg_reduce = [&](float &bv, int &bi) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -784,7 +794,8 @@ constexpr int FS_MMA_WARPS = 4;                 // consumer warps that run the G
 constexpr int FS_STAGES = 4;
 constexpr int FS_ROW_PAD = 16;                  // bytes added to a tile row so that ldmatrix rows fall in different banks
 constexpr int FS_TILE_BYTES = 16 * (SK_KC_MAX * 2 + FS_ROW_PAD);  // 16 weight rows x d_model columns (one K chunk)
-constexpr int FS_XS_BYTES = 40960;              // staged activations in bf16: 8 rows at K <= 2560, 4 rows at K = 5120 (fc2)
+constexpr int FS_XS_PAD = 8;                    // bf16 elements of padding per staged row: see xs_at
+constexpr int FS_XS_BYTES = 4 * (4 * SK_KC_MAX + FS_XS_PAD) * 2;  // staged activations in bf16: 8 rows at K <= 2560, 4 rows at K = 5120 (fc2)
 constexpr int FS_OFF_XS = FS_STAGES * FS_TILE_BYTES;
 constexpr int FS_OFF_BAR = FS_OFF_XS + FS_XS_BYTES;
 constexpr int FS_SMEM = FS_OFF_BAR + 2 * FS_STAGES * 8;
@@ -855,7 +866,7 @@ __device__ __forceinline__ FsJob fs_job(const FusedArgs &a, int j) {
         default: return FsJob{(const bf16 *)w.w2, d, 4 * d};
     }
 }
-__device__ __forceinline__ int fs_row_cap(int K) { return min(SK_MB, FS_XS_BYTES / (2 * K)); }  // activation rows staged per pass
+__device__ __forceinline__ int fs_row_cap(int K) { return min(SK_MB, FS_XS_BYTES / (2 * (K + FS_XS_PAD))); }  // activation rows staged per pass
 
 // producer: every tile this CTA will consume, in consumption order.  A tile = 16 consecutive weight rows x one K chunk of d_model
 // columns; rows are copied one by one (2 d_model bytes each) to a padded pitch so that ldmatrix is bank-conflict free.
@@ -895,85 +906,128 @@ __device__ __noinline__ void fs_produce(const FusedArgs &a, uint32_t ring, uint3
 
 // rows [0, Bd) of the phase input -> xs[Bd][K] in bf16 (the B operand of the tensor-core GEMV).  ln_g != nullptr: LayerNorm over the
 // row (K = d_model); from_tokens: the row is the embedding of the token at `pos` plus the positional row (first phase of the step;
-// CTA 0 also leaves it in dx for the residual).  Everything here is a rolled loop on purpose: this code runs once per phase, and
-// straight-line code that runs once is fetched from L2 line by line (an unrolled register-resident version took 30 us).
+// CTA 0 also leaves it in dx for the residual).  This code runs once per phase, i.e. from a cold instruction cache, so it has to stay
+// short: FS_STAGE_NV pieces per lane is the only unrolled dimension.
+// 16-byte pieces a thread keeps in flight while staging.  The LayerNorm version holds them from the load to the normalised store, and its
+// register count is NOT its own business: with 5 pieces per lane (all eight rows at once) ptxas' interprocedural allocation left the key
+// loop of fs_attn short of registers, its prefetched K / V rows were spilled — i.e. waited for — and both attentions of a layer got
+// 3 - 5 us slower at B = 1, 23 us at B = 8.  3 pieces = four warps per row = four rows per round is the most that leaves fs_attn alone.
+constexpr int FS_STAGE_NV = 3;
+constexpr int FS_STAGE_NV_PLAIN = 3;  // (the plain copy's register count matters in the same way: 4 already costs fs_attn 8 spills)
+// element index of (row m, column k) in the staging buffer.  The row pitch is 2 K + 16 bytes: at 2 K (a multiple of 128) the eight window
+// rows a B fragment reads lie in the same four banks, an 8-way conflict on every fragment load that made the logits 1.5x slower at B = 8
+__device__ __forceinline__ int xs_at(int m, int k, int K) { return m * (K + FS_XS_PAD) + k; }
+
+__device__ __noinline__ void fs_stage_plain(const float *__restrict__ x, int ldx, int K, int Bd, bf16 *xs) {
+    const int tid = threadIdx.x;
+    cbar();  // the previous phase is done with xs
+    // plain f32 -> bf16 copy.  Every thread requests FS_STAGE_NV_PLAIN independent 16-byte pieces before it touches the first one: a rolled
+    // load-convert-store loop pays one L2 round trip (~0.7 us) per iteration, which made a 4-row pass of fc2 cost 7 us
+    const int n4row = K >> 2, n4 = Bd * n4row;
+    const unsigned rcp = 0xffffffffu / (unsigned)n4row + 1u;  // idx / n4row == umulhi(idx, rcp) for idx < 2^16
+#pragma unroll 1
+    for (int base = tid; base < n4; base += FS_CTHREADS * FS_STAGE_NV_PLAIN) {
+        float4 v[FS_STAGE_NV_PLAIN];
+#pragma unroll
+        for (int j = 0; j < FS_STAGE_NV_PLAIN; ++j) {
+            const int idx = base + j * FS_CTHREADS;
+            if (idx < n4) {
+                const int m = (int)__umulhi((unsigned)idx, rcp);
+                v[j] = __ldcg((const float4 *)(x + (size_t)m * ldx) + (idx - m * n4row));  // written by other SMs during this launch: L2, not L1
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < FS_STAGE_NV_PLAIN; ++j) {
+            const int idx = base + j * FS_CTHREADS;
+            if (idx < n4) {
+                const int m = (int)__umulhi((unsigned)idx, rcp);
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v[j].x, v[j].y), hi = __floats2bfloat162_rn(v[j].z, v[j].w);
+                *(uint2 *)&xs[xs_at(m, 4 * (idx - m * n4row), K)] = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
+            }
+        }
+    }
+    cbar();
+}
+
+// LayerNorm (candle_nn: mean, then the centred variance, eps 1e-5), up to four rows per round: 16 / pow2(rows) >= 4 warps share a row,
+// every lane keeps its <= FS_STAGE_NV float4 of the row in registers from the load to the normalised store (one L2 round trip and two
+// barriers per round).  The first version went through a rolled load loop — one L2 round trip per iteration — and cost 5 us + 1.5 us per row.
+// One call = one round of Bd <= 4 rows (the caller shifts the pointers).  Keep this function's register count low: see FS_STAGE_NV.
 __device__ __noinline__ void fs_stage(const FusedArgs &a, const float *__restrict__ x, int ldx, int K, int m_first, int Bd, const float *__restrict__ ln_g,
                                       const float *__restrict__ ln_b, float *__restrict__ ln_out, bool from_tokens, int pos, bf16 *xs, float *stats) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    cbar();  // the previous phase is done with xs
-    if (!ln_g) {
-#pragma unroll 1
-        for (int i = tid * 4; i < Bd * K; i += FS_CTHREADS * 4) {
-            const int m = i / K, k = i - m * K;
-            const float4 t = __ldcg((const float4 *)(x + (size_t)m * ldx + k));  // written by other SMs during this launch: L2, not L1
-            __nv_bfloat162 lo = __floats2bfloat162_rn(t.x, t.y), hi = __floats2bfloat162_rn(t.z, t.w);
-            *(uint2 *)&xs[i] = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
-        }
-        cbar();
-        return;
-    }
-    // LayerNorm, four rows at a time: f32 copy of the rows in the upper half of the staging buffer, bf16 result in the lower half
-    float *tmp = (float *)((uint8_t *)xs + FS_XS_BYTES / 2);
-#pragma unroll 1
-    for (int r0 = 0; r0 < Bd; r0 += 4) {
-        const int nb = min(4, Bd - r0);
-#pragma unroll 1
-        for (int i = tid; i < nb * K; i += FS_CTHREADS) {
-            const int m = i / K, k = i - m * K, b = m_first + r0 + m;
-            float t;
-            if (from_tokens) {
-                uint32_t tok = pos < __ldcg(a.len + b) ? __ldcg(a.tokens + (size_t)b * a.P + pos) : 0u;
-                if (tok >= (uint32_t)a.V) tok = 0;
-                t = __bfloat162float(a.embed[(size_t)tok * K + k]) + a.embed_pos[(size_t)pos * K + k];
-                if (blockIdx.x == 0) a.dx[(size_t)b * K + k] = t;
-            } else {
-                t = __ldcg(x + (size_t)(r0 + m) * ldx + k);
-            }
-            tmp[i] = t;
-        }
-        cbar();
-        if (warp < nb) {  // candle_nn LayerNorm: mean, then the centred variance, eps 1e-5
-            const float *row = tmp + warp * K;
-            float s1 = 0.f, s1b = 0.f, s1c = 0.f, s1d = 0.f;  // four independent chains: the loop is latency-, not throughput-bound
-            int k = lane;
-#pragma unroll 1
-            for (; k + 96 < K; k += 128) { s1 += row[k]; s1b += row[k + 32]; s1c += row[k + 64]; s1d += row[k + 96]; }
-#pragma unroll 1
-            for (; k < K; k += 32) s1 += row[k];
-            s1 = (s1 + s1b) + (s1c + s1d);
+    cbar();  // the previous phase is done with xs, the previous round with the statistics
+    int p2 = 1;
+    while (p2 < Bd) p2 <<= 1;
+    const int wpr = FS_WARPS / p2, r = warp / wpr, n4 = K >> 2, stride = wpr * 32, q0 = (warp - r * wpr) * 32 + lane;
+    {
+    const int nj = (r < Bd && q0 < n4) ? (n4 - q0 + stride - 1) / stride : 0;  // float4 pieces of this lane
+    // the row: x, or (first phase of the step) the positional row plus the embedding of the token at `pos`
+    const float4 *xp = (const float4 *)(from_tokens ? a.embed_pos + (size_t)pos * K : x + (size_t)r * ldx) + q0;
+    float4 v[FS_STAGE_NV];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            const float mean = s1 / (float)K;
-            float s2 = 0.f, s2b = 0.f, s2c = 0.f, s2d = 0.f;
-            k = lane;
-#pragma unroll 1
-            for (; k + 96 < K; k += 128) {
-                const float d0 = row[k] - mean, d1 = row[k + 32] - mean, d2 = row[k + 64] - mean, d3 = row[k + 96] - mean;
-                s2 += d0 * d0; s2b += d1 * d1; s2c += d2 * d2; s2d += d3 * d3;
-            }
-#pragma unroll 1
-            for (; k < K; k += 32) {
-                const float dv = row[k] - mean;
-                s2 += dv * dv;
-            }
-            s2 = (s2 + s2b) + (s2c + s2d);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            if (lane == 0) {
-                stats[2 * warp] = mean;
-                stats[2 * warp + 1] = rsqrtf(s2 / (float)K + 1e-5f);
-            }
-        }
-        cbar();
-#pragma unroll 1
-        for (int i = tid; i < nb * K; i += FS_CTHREADS) {
-            const int m = i / K, k = i - m * K;
-            const float y = (tmp[i] - stats[2 * m]) * stats[2 * m + 1] * __ldg(ln_g + k) + __ldg(ln_b + k);
-            xs[(r0 + m) * K + k] = __float2bfloat16(y);
-            if (ln_out && blockIdx.x == 0) ln_out[(size_t)(r0 + m) * K + k] = y;
-        }
-        cbar();
+    for (int j = 0; j < FS_STAGE_NV; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nj) v[j] = __ldcg(xp + j * stride);  // (x is written by other SMs during this launch: L2, not L1)
     }
+    if (from_tokens) {
+        const int b = m_first + r;
+        uint32_t tok = 0u;
+        if (nj > 0 && pos < __ldcg(a.len + b)) tok = __ldcg(a.tokens + (size_t)b * a.P + pos);
+        if (tok >= (uint32_t)a.V) tok = 0;
+        const uint2 *er = (const uint2 *)(a.embed + (size_t)tok * K) + q0;
+        float4 *dxp = (float4 *)(a.dx + (size_t)b * K) + q0;
+#pragma unroll
+        for (int j = 0; j < FS_STAGE_NV; ++j)
+            if (j < nj) {
+                const uint2 eb = __ldg(er + j * stride);
+                const float2 e01 = __bfloat1622float2(*(const __nv_bfloat162 *)&eb.x), e23 = __bfloat1622float2(*(const __nv_bfloat162 *)&eb.y);
+                v[j].x += e01.x; v[j].y += e01.y; v[j].z += e23.x; v[j].w += e23.y;
+                if (blockIdx.x == 0) dxp[j * stride] = v[j];
+            }
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < FS_STAGE_NV; ++j)
+        if (j < nj) s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    if (lane == 0) stats[warp] = s1;
+    cbar();
+    float mean = 0.f;
+#pragma unroll 1
+    for (int w = 0; w < wpr; ++w) mean += stats[r * wpr + w];
+    mean /= (float)K;
+    float s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < FS_STAGE_NV; ++j)
+        if (j < nj) {
+            const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+            s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) stats[FS_WARPS + warp] = s2;
+    cbar();
+    float var = 0.f;
+#pragma unroll 1
+    for (int w = 0; w < wpr; ++w) var += stats[FS_WARPS + r * wpr + w];
+    const float rstd = rsqrtf(var / (float)K + 1e-5f);
+    const float4 *gp = (const float4 *)ln_g + q0, *bp = (const float4 *)ln_b + q0;
+    bf16 *xo = xs + xs_at(r, 4 * q0, K);
+    float4 *lo_p = (ln_out && blockIdx.x == 0) ? (float4 *)(ln_out + (size_t)r * K) + q0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < FS_STAGE_NV; ++j)
+        if (j < nj) {
+            const float4 g = __ldg(gp + j * stride), bt = __ldg(bp + j * stride);
+            const float4 y = make_float4((v[j].x - mean) * rstd * g.x + bt.x, (v[j].y - mean) * rstd * g.y + bt.y,
+                                         (v[j].z - mean) * rstd * g.z + bt.z, (v[j].w - mean) * rstd * g.w + bt.w);
+            __nv_bfloat162 lo = __floats2bfloat162_rn(y.x, y.y), hi = __floats2bfloat162_rn(y.z, y.w);
+            *(uint2 *)(xo + 4 * j * stride) = make_uint2(*(uint32_t *)&lo, *(uint32_t *)&hi);
+            if (lo_p) lo_p[j * stride] = y;
+        }
+    }
+    cbar();
 }
 
 // consumer side of one weight matrix: out[m][n] = epilogue(sum_k x[m][k] W[n][k]) for every window row, on the tensor cores:
@@ -993,7 +1047,14 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
 #pragma unroll 1
     for (int m0 = 0; m0 < a.B; m0 += cap) {
         const int Bd = min(cap, a.B - m0);
-        fs_stage(a, x ? x + (size_t)m0 * ldx : nullptr, ldx, K, m0, Bd, ln_g, ln_b, ln_out ? ln_out + (size_t)m0 * K : nullptr, from_tokens, pos, xs, stats);
+        if (ln_g) {
+#pragma unroll 1
+            for (int r0 = 0; r0 < Bd; r0 += 4)  // four rows per round
+                fs_stage(a, x ? x + (size_t)(m0 + r0) * ldx : nullptr, ldx, K, m0 + r0, min(4, Bd - r0), ln_g, ln_b, ln_out ? ln_out + (size_t)(m0 + r0) * K : nullptr,
+                         from_tokens, pos, xs + xs_at(r0, 0, K), stats);
+        } else {
+            fs_stage_plain(x + (size_t)m0 * ldx, ldx, K, Bd, xs);
+        }
         int gi = 0;
         if (n_chunks == FS_MMA_WARPS) {
             // K = 4 d_model (fc2): a group's four K chunks are four consecutive ring tiles; MMA warp w takes chunk w of EVERY group, so the four
@@ -1018,7 +1079,7 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
                     }
                 }
                 const int bn = lane >> 2;
-                const bf16 *xk = xs + (bn < Bd ? bn : 0) * K + (lane & 3) * 2 + warp * KC;
+                const bf16 *xk = xs + xs_at(bn < Bd ? bn : 0, (lane & 3) * 2 + warp * KC, K);
                 const unsigned ct = cnt + warp, st = ct % FS_STAGES;
                 ptx::mbar_wait(full0 + 8 * st, (ct / FS_STAGES) & 1);
                 const uint32_t arow = ring + st * FS_TILE_BYTES + (lane & 15) * pitch + (lane >> 4) * 16;
@@ -1082,7 +1143,7 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
                 }
             }
             const int bn = lane >> 2;  // window row (B operand column) this lane feeds
-            const bf16 *xrow = xs + (bn < Bd ? bn : 0) * K + (lane & 3) * 2;
+            const bf16 *xrow = xs + xs_at(bn < Bd ? bn : 0, (lane & 3) * 2, K);
 #pragma unroll 1
             for (int c = 0; c < n_chunks; ++c, ++cnt) {
                 const unsigned s = cnt % FS_STAGES;
@@ -1135,8 +1196,13 @@ __device__ __forceinline__ void osm_merge_fast(float &m, float &l, float *acc, f
     m = mn;
 }
 
-__device__ __noinline__ void fs_attn_cta(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int H, int B, int n_keys, bool append,
-                                         const float *__restrict__ newkv, int ldkv, int koff, int voff, float *__restrict__ out, int ldo, float *sm) {
+// (few arguments on purpose, here and in fs_attn: the phase functions get the registers the kernel body does not keep live across the
+// call, and the key loop spills its prefetched rows — which serialises the prefetch — as soon as it is a handful short.  `append`: self
+// attention, q = the [B][3 d] QKV rows whose k and v parts join the cache at position n_keys - 1.)
+__device__ __noinline__ void fs_attn_cta(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int B, int n_keys, bool append,
+                                         float *__restrict__ out, float *sm) {
+    const int H = d / HEAD_DIM, ldo = d, ldkv = ldq, koff = d, voff = 2 * d;
+    const float *newkv = q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l8 = lane & 7, grp = lane >> 3;
     const unsigned gmask = 0xffu << (grp * 8);
 #pragma unroll 1
@@ -1226,9 +1292,10 @@ __device__ __noinline__ void fs_attn_cta(const float *__restrict__ q, int ldq, b
 // softmax, writes (m, l, o[64]) to the workspace, and the warp that takes the last ticket of a (window, head) folds the S partials
 // into `out` (no grid barrier between the splits and the merge).  Rolled loops, ~2 KB of code: the 128-thread version shared with the
 // stand-alone kernels was 17 KB that each phase executed once, out of a cold instruction cache.
-__device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int H, int B, int n_keys, bool append,
-                                     const float *__restrict__ newkv, int ldkv, int koff, int voff, float *__restrict__ ws, unsigned *__restrict__ cnt, int S,
-                                     float *__restrict__ out, int ldo) {
+__device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int B, int n_keys, bool append,
+                                     float *__restrict__ ws, unsigned *__restrict__ cnt, int S, float *__restrict__ out) {
+    const int H = d / HEAD_DIM, ldo = d, ldkv = ldq, koff = d, voff = 2 * d;
+    const float *newkv = q;
     const int lane = threadIdx.x & 31, gw = blockIdx.x * FS_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * FS_WARPS;
     const int n_items = H * B * S;
 #pragma unroll 1
@@ -1340,6 +1407,85 @@ __device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 
     }
 }
 
+// ---- select of the fused step (B <= FS_SEL_MAXB windows): one window per WARP (vocabulary chunk = this CTA), so the windows of a
+// batch are folded in parallel and without block barriers (the block-wide bodies take them one after the other: 14 + 48 us at B = 8).
+// The statistics phase leaves the chunk's suppression mask (slot 0) and every window's logits (slot b + 1) in the idle activation staging
+// buffer for the candidates phase of the same CTA.
+constexpr int FS_SEL_PER = 384;  // largest vocabulary chunk (V / grid) this path caches: 12 values per lane
+constexpr int FS_SEL_NP = 5;     // chunk partials per lane: grid <= 160
+constexpr int FS_SEL_MAXB = FS_XS_BYTES / (FS_SEL_PER * 4) - 1;
+
+__device__ __noinline__ void fs_select_stats_w(const FusedArgs &a, float *sm) {
+    const int tid = threadIdx.x, lane = tid & 31, nch = gridDim.x, V = a.V;
+    const int per = (V + nch - 1) / nch, lo = blockIdx.x * per, hi = min(V, lo + per);
+    if (lo + tid < hi) sm[tid] = a.sp.suppress[lo + tid];  // per <= FS_SEL_PER <= FS_CTHREADS
+#pragma unroll 1
+    for (int b = tid >> 5; b < a.B; b += FS_WARPS) {
+        const float *x = a.logits + (size_t)b * V + lo + lane;
+        float *xl = sm + (b + 1) * FS_SEL_PER + lane;
+        float v[FS_SEL_PER / 32], lm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < FS_SEL_PER / 32; ++j) {  // all the loads of the lane before the first use
+            v[j] = lo + lane + 32 * j < hi ? __ldcg(x + 32 * j) : -INFINITY;
+            lm = fmaxf(lm, v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+        float ls = 0.f;
+#pragma unroll
+        for (int j = 0; j < FS_SEL_PER / 32; ++j)
+            if (lo + lane + 32 * j < hi) {
+                ls += expf(v[j] - lm);
+                xl[32 * j] = v[j];
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        if (lane == 0) a.sel_a[b * nch + blockIdx.x] = make_float2(lm, ls);
+    }
+}
+
+__device__ __noinline__ void fs_select_cand_w(const FusedArgs &a, const float *sm) {
+    const SelectParams &sp = a.sp;
+    const int tid = threadIdx.x, lane = tid & 31, nch = gridDim.x, V = a.V;
+    const int per = (V + nch - 1) / nch, lo = blockIdx.x * per, n = min(V, lo + per) - lo;
+#pragma unroll 1
+    for (int b = tid >> 5; b < a.B; b += FS_WARPS) {
+        if (__ldcg(sp.done + b)) continue;
+        const int len = __ldcg(sp.len + b), last_ts = __ldcg(sp.last_ts + b);
+        float2 u[FS_SEL_NP];
+        float M = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < FS_SEL_NP; ++j) {
+            u[j] = lane + 32 * j < nch ? __ldcg(a.sel_a + b * nch + lane + 32 * j) : make_float2(-INFINITY, 0.f);
+            M = fmaxf(M, u[j].x);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        float S = 0.f;
+#pragma unroll
+        for (int j = 0; j < FS_SEL_NP; ++j) S += u[j].y * expf(u[j].x - M);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        int mode_a, mode_b;
+        cand_modes(sp, b, len, last_ts, mode_a, mode_b);
+        const float *xl = sm + (b + 1) * FS_SEL_PER;
+        float ts = 0.f, mt = -INFINITY, ba = -INFINITY, bb = -INFINITY;
+        int ia = -1, ib = -1;
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) cand_update(sp, mode_a, mode_b, last_ts, lo + i, expf(xl[i] - M) / S, sm[i], ts, mt, ba, bb, ia, ib);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, ba, o), pv = __shfl_xor_sync(0xffffffffu, bb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, ia, o), pi = __shfl_xor_sync(0xffffffffu, ib, o);
+            if (ov > ba || (ov == ba && oi > ia)) { ba = ov; ia = oi; }
+            if (pv > bb || (pv == bb && pi > ib)) { bb = pv; ib = pi; }
+            ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+        }
+        if (lane == 0) a.sel_b[b * nch + blockIdx.x] = SelCand{ts, mt, ba, bb, ia, ib};
+    }
+}
+
 __global__ void __launch_bounds__(FS_THREADS, 1)
 decoder_step_fused_kernel(const FusedArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1349,6 +1495,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
     __shared__ float att_sm[FS_WARPS * 8 * 10];  // per-warp (m, l, o[8]) partials of fs_attn_cta
     __shared__ __align__(16) float kpart[2 * 3 * 32 * 4];  // K-split partial fragments of fc2 (fs_gemv)
     __shared__ volatile int go_step;
+    __shared__ DecLayer w_sm;
     const int tid = threadIdx.x;
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t full0 = sbase + FS_OFF_BAR, empty0 = full0 + 8 * FS_STAGES;
@@ -1388,7 +1535,12 @@ decoder_step_fused_kernel(const FusedArgs a) {
 #endif
     DEC_STAMP();
     for (int l = 0; l < a.L; ++l) {
-        const DecLayer w = a.layers[l];
+        // the layer's 20 pointers live in shared memory, not in registers: whatever the kernel body keeps live across the calls below is
+        // taken from the register window of the (non-inlined) phase functions, and the attention loop spilled once it lost ~20 registers
+        cbar();
+        if (tid < (int)(sizeof(DecLayer) / 8)) ((unsigned long long *)&w_sm)[tid] = ((const unsigned long long *)(a.layers + l))[tid];
+        cbar();
+        const DecLayer &w = w_sm;
         bf16 *skv = a.self_kv + (size_t)l * a.max_batch * P * 2 * d;
         bf16 *ckv = a.cross_kv + (size_t)l * a.max_batch * T * 2 * d;
         SkinnyEpi e{};
@@ -1396,8 +1548,8 @@ decoder_step_fused_kernel(const FusedArgs a) {
         fs_gemv(a, 6 * l + 0, l == 0 ? nullptr : a.dx, d, w.ln1g, w.ln1b, nullptr, l == 0, pos, e, smem, full0, empty0, cnt, ln_stats, kpart);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
-        if (B * H <= (int)gridDim.x) fs_attn_cta(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.dattn, d, att_sm);
-        else fs_attn(a.dqkv, 3 * d, skv, P, d, H, B, pos + 1, true, a.dqkv, 3 * d, d, 2 * d, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, d);
+        if (B * H <= (int)gridDim.x) fs_attn_cta(a.dqkv, 3 * d, skv, P, d, B, pos + 1, true, a.dattn, att_sm);
+        else fs_attn(a.dqkv, 3 * d, skv, P, d, B, pos + 1, true, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
@@ -1411,7 +1563,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         // (1500 keys per pair are too many for one CTA's 16 loads in flight: 19.5 us against 14.6 us split over the grid)
-        fs_attn(a.dq, d, ckv, T, d, H, B, T, false, nullptr, 0, 0, 0, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn, d);
+        fs_attn(a.dq, d, ckv, T, d, B, T, false, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
@@ -1438,18 +1590,10 @@ decoder_step_fused_kernel(const FusedArgs a) {
     grid_sync(a.sync_counter, target);
     DEC_STAMP();
     // ---- greedy select (the three phases of select_*_kernel; FS_CTHREADS threads through the consumers' named barrier) ----
-#pragma unroll 1
-    for (int it = blockIdx.x; it < B * nch; it += gridDim.x) {
-        cbar();
-        select_stats_body<FS_BAR_ID, FS_CTHREADS>(a.logits, V, a.sel_a, it / nch, it % nch, nch, red);
-    }
+    fs_select_stats_w(a, (float *)(smem + FS_OFF_XS));
     grid_sync(a.sync_counter, target);
     DEC_STAMP();
-#pragma unroll 1
-    for (int it = blockIdx.x; it < B * nch; it += gridDim.x) {
-        cbar();
-        select_cand_body<FS_BAR_ID, FS_CTHREADS>(a.sp, a.sel_a, a.sel_b, it / nch, it % nch, nch, red, red_i);
-    }
+    fs_select_cand_w(a, (const float *)(smem + FS_OFF_XS));
     grid_sync(a.sync_counter, target);
     DEC_STAMP();
     if (tid < 32)
@@ -1658,8 +1802,12 @@ int decoder_select(nb200_ctx *ctx, int n_windows, int greedy) {
 // bf16 contexts only.
 bool decoder_fused_supported(const nb200_ctx *ctx) {
     const nb200_config &c = ctx->cfg;
-    return ctx->compute == NB200_BF16 && c.d_model % 16 == 0 && c.d_model <= SK_KC_MAX && c.decoder_attention_heads * HEAD_DIM == c.d_model;
+    const int nch = ctx->sm_count;  // one vocabulary chunk per CTA in the select (fs_select_*_w)
+    if (nch < 1 || nch > 32 * FS_SEL_NP || (c.vocab_size + nch - 1) / nch > FS_SEL_PER) return false;
+    return ctx->compute == NB200_BF16 && c.d_model % 16 == 0 && c.d_model <= SK_KC_MAX && SK_KC_MAX <= FS_STAGE_NV * 512 && c.decoder_attention_heads * HEAD_DIM == c.d_model;
 }
+
+int decoder_fused_max_windows() { return FS_SEL_MAXB; }  // windows whose logits chunk fits the staging buffer during the select
 
 int decoder_fused_ws_floats(const nb200_ctx *ctx) { return ctx->cfg.max_batch * ctx->cfg.decoder_attention_heads * FS_MAX_SPLITS * ATT_WS; }
 
@@ -1682,6 +1830,7 @@ int decoder_fused_prepare(nb200_ctx *ctx) {
 int decoder_step_fused(nb200_ctx *ctx, int n_windows, int n_steps) {
     const nb200_config &c = ctx->cfg;
     NB_TRY(decoder_fused_prepare(ctx));
+    if (n_windows < 1 || n_windows > FS_SEL_MAXB) return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "fused decoder step: %d windows (at most %d)", n_windows, FS_SEL_MAXB);
     void *kern = (void *)decoder_step_fused_kernel;
     FusedArgs a{};
     a.B = n_windows; a.d = c.d_model; a.V = c.vocab_size; a.P = c.max_target_positions; a.T = c.max_source_positions;
