@@ -794,8 +794,10 @@ constexpr int FS_MMA_WARPS = 4;                 // consumer warps that run the G
 constexpr int FS_STAGES = 4;
 constexpr int FS_ROW_PAD = 16;                  // bytes added to a tile row so that ldmatrix rows fall in different banks
 constexpr int FS_TILE_BYTES = 16 * (SK_KC_MAX * 2 + FS_ROW_PAD);  // 16 weight rows x d_model columns (one K chunk)
+constexpr int FS_ATT_ST = 3;                    // stages (of four keys) a warp of fs_attn keeps in flight: 3 KB per warp in the staging buffer
 constexpr int FS_XS_PAD = 8;                    // bf16 elements of padding per staged row: see xs_at
-constexpr int FS_XS_BYTES = 4 * (4 * SK_KC_MAX + FS_XS_PAD) * 2;  // staged activations in bf16: 8 rows at K <= 2560, 4 rows at K = 5120 (fc2)
+constexpr int FS_XS_BYTES = 16 * FS_ATT_ST * 1024;  // staged activations in bf16: 8 rows at K <= 2560, 4 rows at K = 5120 (fc2); the attention FIFOs
+static_assert(FS_XS_BYTES >= 4 * (4 * SK_KC_MAX + FS_XS_PAD) * 2, "fc2 stages four rows per pass");
 constexpr int FS_OFF_XS = FS_STAGES * FS_TILE_BYTES;
 constexpr int FS_OFF_BAR = FS_OFF_XS + FS_XS_BYTES;
 constexpr int FS_SMEM = FS_OFF_BAR + 2 * FS_STAGES * 8;
@@ -1293,86 +1295,106 @@ __device__ __noinline__ void fs_attn_cta(const float *__restrict__ q, int ldq, b
 // into `out` (no grid barrier between the splits and the merge).  Rolled loops, ~2 KB of code: the 128-thread version shared with the
 // stand-alone kernels was 17 KB that each phase executed once, out of a cold instruction cache.
 __device__ __noinline__ void fs_attn(const float *__restrict__ q, int ldq, bf16 *__restrict__ cache, int Tmax, int d, int B, int n_keys, bool append,
-                                     float *__restrict__ ws, unsigned *__restrict__ cnt, int S, float *__restrict__ out) {
-    const int H = d / HEAD_DIM, ldo = d, ldkv = ldq, koff = d, voff = 2 * d;
-    const float *newkv = q;
-    const int lane = threadIdx.x & 31, gw = blockIdx.x * FS_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * FS_WARPS;
+                                     float *__restrict__ ws, unsigned *__restrict__ cnt, int S, float *__restrict__ out, uint8_t *stage) {
+    const int H = d / HEAD_DIM, ldo = d;
+    const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, gw = blockIdx.x * FS_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * FS_WARPS;
+    const unsigned gmask = 0xffu << (grp * 8);
     const int n_items = H * B * S;
+    // this lane's FIFO slots in the (idle) activation staging buffer: FS_ATT_ST stages of [K 16 B | V 16 B] per lane.  Eight lanes share a
+    // key (16 bytes of the K and of the V row each), so one stage is four keys of the warp; the rows travel by cp.async, FS_ATT_ST stages
+    // ahead — in registers (the first version) four keys per warp were all that could be in flight, 2.4 MB over the whole GPU, which is
+    // 2 TB/s at HBM latency: 30 us for the cross attention of eight windows.
+    const uint32_t slot = ptx::smem_u32(stage) + (threadIdx.x >> 5) * (FS_ATT_ST * 1024) + lane * 16;
 #pragma unroll 1
     for (int it = gw; it < n_items; it += n_warps) {
         const int sp = it % S, h = (it / S) % H, b = it / (S * H);
         const int chunk = (n_keys + S - 1) / S, k0 = sp * chunk;
         int k1 = min(n_keys, k0 + chunk);
-        bf16 *cb = cache + (size_t)b * Tmax * 2 * d + h * HEAD_DIM + lane * 2;
-        const float2 qv = __ldcg((const float2 *)(q + (size_t)b * ldq + h * HEAD_DIM + lane * 2));
-        float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
-        int j = k0;
-        if (append && k1 == n_keys && k1 > k0) {  // this split owns the position being decoded: k, v come from the QKV GEMV and join the cache
-            const int jn = n_keys - 1;
-            const float2 kf = __ldcg((const float2 *)(newkv + (size_t)b * ldkv + koff + h * HEAD_DIM + lane * 2));
-            const float2 vf = __ldcg((const float2 *)(newkv + (size_t)b * ldkv + voff + h * HEAD_DIM + lane * 2));
-            const __nv_bfloat162 kb = __floats2bfloat162_rn(kf.x, kf.y), vb = __floats2bfloat162_rn(vf.x, vf.y);
-            *(__nv_bfloat162 *)(cb + (size_t)jn * 2 * d) = kb;
-            *(__nv_bfloat162 *)(cb + (size_t)jn * 2 * d + d) = vb;
-            const float2 kr = __bfloat1622float2(kb), vr = __bfloat1622float2(vb);  // what every later step will read
-            float sd = qv.x * kr.x + qv.y * kr.y;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-            m = sd; l = 1.f; a0 = vr.x; a1 = vr.y;
-            k1 = jn;  // the loop below covers the cached keys only
+        bf16 *cb = cache + (size_t)b * Tmax * 2 * d + h * HEAD_DIM + l8 * 8;
+        float qr[8];
+        {
+            const float *qp = q + (size_t)b * ldq + h * HEAD_DIM + l8 * 8;
+            const float4 qa = __ldcg((const float4 *)qp), qc = __ldcg((const float4 *)qp + 1);
+            qr[0] = qa.x; qr[1] = qa.y; qr[2] = qa.z; qr[3] = qa.w; qr[4] = qc.x; qr[5] = qc.y; qr[6] = qc.z; qr[7] = qc.w;
         }
-        // four keys per iteration (their dot products reduce through the same five shuffle rounds, then ONE online-softmax update), the next
-        // four K / V rows requested before this group's softmax chain: the loop is a chain of L2 round trips and shuffle latencies, not of work
-        __nv_bfloat162 kr[4], vr[4];
-        auto load4 = [&](int jj) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int jt = jj + t < k1 ? jj + t : k1 - 1;  // past the end: re-read the last row (its score is masked below)
-                kr[t] = *(const __nv_bfloat162 *)(cb + (size_t)jt * 2 * d);
-                vr[t] = *(const __nv_bfloat162 *)(cb + (size_t)jt * 2 * d + d);
+        auto issue = [&](int i4) {  // stage i4 % FS_ATT_ST <- keys k0 + 4 i4 .. + 3 (always one group, possibly empty: the wait below counts groups)
+            const int jj = k0 + 4 * i4 + grp;
+            if (jj < k1) {
+                const bf16 *src = cb + (size_t)jj * 2 * d;
+                const uint32_t dst = slot + (i4 % FS_ATT_ST) * 1024;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(src + d) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        if (j < k1) load4(j);
+        float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+        const bool own_new = append && k1 == n_keys && k1 > k0;  // this split owns the position being decoded
+        if (own_new) k1 = n_keys - 1;                           // the staged loop covers the cached keys only
 #pragma unroll 1
-        for (; j < k1; j += 4) {
-            float sc[4];
-            float2 vf[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 kf = __bfloat1622float2(kr[t]);
-                vf[t] = __bfloat1622float2(vr[t]);
-                sc[t] = qv.x * kf.x + qv.y * kf.y;
+        for (int i4 = 0; i4 < FS_ATT_ST; ++i4) issue(i4);
+        if (own_new && grp == 0) {  // k, v of the new position come from the QKV GEMV (q = the [B][3 d] rows) and join the cache
+            const float *kp = q + (size_t)b * ldq + d + h * HEAD_DIM + l8 * 8, *vp = kp + d;
+            const float4 k0f = __ldcg((const float4 *)kp), k1f = __ldcg((const float4 *)kp + 1), v0f = __ldcg((const float4 *)vp), v1f = __ldcg((const float4 *)vp + 1);
+            const __nv_bfloat162 t0 = __floats2bfloat162_rn(k0f.x, k0f.y), t1 = __floats2bfloat162_rn(k0f.z, k0f.w), t2 = __floats2bfloat162_rn(k1f.x, k1f.y),
+                                 t3 = __floats2bfloat162_rn(k1f.z, k1f.w);
+            const __nv_bfloat162 u0 = __floats2bfloat162_rn(v0f.x, v0f.y), u1 = __floats2bfloat162_rn(v0f.z, v0f.w), u2 = __floats2bfloat162_rn(v1f.x, v1f.y),
+                                 u3 = __floats2bfloat162_rn(v1f.z, v1f.w);
+            *(uint4 *)(cb + (size_t)(n_keys - 1) * 2 * d) = make_uint4(*(const uint32_t *)&t0, *(const uint32_t *)&t1, *(const uint32_t *)&t2, *(const uint32_t *)&t3);
+            *(uint4 *)(cb + (size_t)(n_keys - 1) * 2 * d + d) = make_uint4(*(const uint32_t *)&u0, *(const uint32_t *)&u1, *(const uint32_t *)&u2, *(const uint32_t *)&u3);
+            const float2 a = __bfloat1622float2(t0), c = __bfloat1622float2(t1), e = __bfloat1622float2(t2), g = __bfloat1622float2(t3);  // what every later step reads
+            float sd = qr[0] * a.x + qr[1] * a.y + qr[2] * c.x + qr[3] * c.y + qr[4] * e.x + qr[5] * e.y + qr[6] * g.x + qr[7] * g.y;
+            sd += __shfl_xor_sync(gmask, sd, 1);
+            sd += __shfl_xor_sync(gmask, sd, 2);
+            sd += __shfl_xor_sync(gmask, sd, 4);
+            const float2 v0 = __bfloat1622float2(u0), v1 = __bfloat1622float2(u1), v2 = __bfloat1622float2(u2), v3 = __bfloat1622float2(u3);
+            m = sd; l = 1.f;
+            acc[0] = v0.x; acc[1] = v0.y; acc[2] = v1.x; acc[3] = v1.y; acc[4] = v2.x; acc[5] = v2.y; acc[6] = v3.x; acc[7] = v3.y;
+        }
+        const int n4 = (k1 - k0 + 3) >> 2;  // (<= 0: an empty split)
+#pragma unroll 1
+        for (int i4 = 0; i4 < n4; ++i4) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(FS_ATT_ST - 1) : "memory");  // the oldest stage has landed (each lane reads its own copies)
+            if (k0 + 4 * i4 + grp < k1) {
+                uint4 ku, vu;
+                const uint32_t src = slot + (i4 % FS_ATT_ST) * 1024;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ku.x), "=r"(ku.y), "=r"(ku.z), "=r"(ku.w) : "r"(src));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vu.x), "=r"(vu.y), "=r"(vu.z), "=r"(vu.w) : "r"(src + 512));
+                const float2 kf0 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.x), kf1 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.y);
+                const float2 kf2 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.z), kf3 = __bfloat1622float2(*(const __nv_bfloat162 *)&ku.w);
+                float sd = qr[0] * kf0.x + qr[1] * kf0.y + qr[2] * kf1.x + qr[3] * kf1.y + qr[4] * kf2.x + qr[5] * kf2.y + qr[6] * kf3.x + qr[7] * kf3.y;
+                sd += __shfl_xor_sync(gmask, sd, 1);  // group-local mask: the last stage may not have a key for every group
+                sd += __shfl_xor_sync(gmask, sd, 2);
+                sd += __shfl_xor_sync(gmask, sd, 4);
+                const float mn = fmaxf(m, sd);
+                const float al = __expf(m - mn), pw = __expf(sd - mn);  // m = -inf on the first key: al = 0
+                const float2 vf0 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.x), vf1 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.y);
+                const float2 vf2 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.z), vf3 = __bfloat1622float2(*(const __nv_bfloat162 *)&vu.w);
+                l = l * al + pw;
+                acc[0] = acc[0] * al + pw * vf0.x; acc[1] = acc[1] * al + pw * vf0.y; acc[2] = acc[2] * al + pw * vf1.x; acc[3] = acc[3] * al + pw * vf1.y;
+                acc[4] = acc[4] * al + pw * vf2.x; acc[5] = acc[5] * al + pw * vf2.y; acc[6] = acc[6] * al + pw * vf3.x; acc[7] = acc[7] * al + pw * vf3.y;
+                m = mn;
             }
-            const int left = k1 - j;
-            if (j + 4 < k1) load4(j + 4);
+            issue(i4 + FS_ATT_ST);  // refill the stage just read
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // (only empty groups are left)
+        __syncwarp();
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 8; o <= 16; o <<= 1) {  // the four key groups of the warp
+            float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o), a2[8];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) sc[t] += __shfl_xor_sync(0xffffffffu, sc[t], o);
-            }
-#pragma unroll
-            for (int t = 1; t < 4; ++t)
-                if (t >= left) sc[t] = -INFINITY;
-            const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));
-            const float al = __expf(m - mn);  // m = -inf on the first group: 0
-            float ps = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float pt = __expf(sc[t] - mn);
-                ps += pt;
-                o0 = fmaf(pt, vf[t].x, o0);
-                o1 = fmaf(pt, vf[t].y, o1);
-            }
-            l = l * al + ps;
-            a0 = a0 * al + o0;
-            a1 = a1 * al + o1;
-            m = mn;
+            for (int t = 0; t < 8; ++t) a2[t] = __shfl_xor_sync(0xffffffffu, acc[t], o);
+            osm_merge_fast(m, l, acc, m2, l2, a2);
         }
         float *wsb = ws + ((size_t)b * H + h) * S * ATT_WS;
         {
             float *o = wsb + (size_t)sp * ATT_WS;
             if (lane == 0) { o[0] = m; o[1] = l; }
-            *(float2 *)(o + 2 + lane * 2) = make_float2(a0, a1);
+            if (grp == 0) {
+#pragma unroll
+                for (int t = 0; t < 8; t += 2) *(float2 *)(o + 2 + l8 * 8 + t) = make_float2(acc[t], acc[t + 1]);
+            }
         }
         __threadfence();
         __syncwarp();
@@ -1549,7 +1571,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         if (B * H <= (int)gridDim.x) fs_attn_cta(a.dqkv, 3 * d, skv, P, d, B, pos + 1, true, a.dattn, att_sm);
-        else fs_attn(a.dqkv, 3 * d, skv, P, d, B, pos + 1, true, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn);
+        else fs_attn(a.dqkv, 3 * d, skv, P, d, B, pos + 1, true, a.attn_ws, a.attn_cnt, FS_SELF_SPLITS, a.dattn, smem + FS_OFF_XS);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};
@@ -1563,7 +1585,7 @@ decoder_step_fused_kernel(const FusedArgs a) {
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         // (1500 keys per pair are too many for one CTA's 16 loads in flight: 19.5 us against 14.6 us split over the grid)
-        fs_attn(a.dq, d, ckv, T, d, B, T, false, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn);
+        fs_attn(a.dq, d, ckv, T, d, B, T, false, a.attn_ws, a.attn_cnt, a.cross_splits, a.dattn, smem + FS_OFF_XS);
         grid_sync(a.sync_counter, target);
         DEC_STAMP();
         e = SkinnyEpi{};

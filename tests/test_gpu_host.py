@@ -322,6 +322,28 @@ def test_quantized_gguf_checkpoint_equals_its_dequantised_weights(lib, tmp_path)
     b.ctx.close()
 
 
+def test_fused_decode_large_batch(lib):
+    """25 windows of the planted tiny.en model: 25 x 6 (window, head) pairs are more than the fused step has CTAs, so self attention
+    takes the split-K path whose last split appends the new position to the cache; the batch also needs four staging passes per
+    GEMV and two rounds of the one-window-per-warp select.  Tokens must equal the plan and the per-operation kernels' output."""
+    c, st, w, plan = planted("tiny.en")
+    B = 25
+    ctx = ffi.Context(c, compute="bf16", max_batch=B)
+    ctx.set_mel_filters(filters.mel_filters(80))
+    ctx.load_weights(w)
+    ctx.set_tokens(st.sot, st.eot, st.task, st.lang, st.no_speech, st.no_timestamps, st.ts_zero, st.ts_one)
+    kinds = ["gauss", "uniform", "bursts"]
+    ctx.transcode_batch(np.stack([synth.synth_pcm(kinds[i % 3], i) for i in range(B)]), want_output=False)
+    want = [st.sot, st.lang, st.task] + [plan[p] for p in range(2, 9)]
+    fused = ctx.decode(B, 0.0)
+    ctx.set_decode_mode(True)
+    separate = ctx.decode(B, 0.0)
+    for b in range(B):
+        assert fused[b]["tokens"] == want == separate[b]["tokens"], b
+        assert abs(fused[b]["avg_logprob"] - separate[b]["avg_logprob"]) < 5e-3
+    ctx.close()
+
+
 def test_fused_and_separate_decode_agree(lib):
     """The fused cooperative step kernel against the per-operation kernels (nb200_set_decode_mode) on three windows in lock-step:
     a planted, confident decoder gives identical tokens; a random-init decoder run to the stop rule (max_target_positions - 1: 28 launches
