@@ -344,6 +344,32 @@ def test_fused_decode_large_batch(lib):
     ctx.close()
 
 
+def test_fused_decode_wide_model(lib):
+    """distil-large-v3's decoder shape (d_model 1280, 20 heads, 2 layers, 128 mel bins, vocabulary 51 866) over a 2-layer encoder, planted,
+    nine windows: every lane of the LayerNorm staging holds three float4 pieces, the batch needs a second GEMV pass of one row, fc2 three
+    passes, and 9 x 20 (window, head) pairs send self attention down the split-K path.  Fused == per-operation kernels == plan."""
+    c = synth.model_config("distil-large-v3")
+    c["encoder_layers"] = 2
+    st = special_tokens_for_vocab(c["vocab_size"])
+    ts = lambda s: st.no_timestamps + 1 + int(round(s / 0.02))
+    plan = {0: 7, 1: 8, 2: ts(0.0), 3: 100, 4: 200, 5: ts(2.0), 6: ts(2.02), 7: 300, 8: st.eot}
+    w = synth.plant_decoder_plan(synth.synth_weights(c, seed=1, embed_scale=1.0), c, plan)
+    B = 9
+    ctx = ffi.Context(c, compute="bf16", max_batch=B)
+    ctx.set_mel_filters(filters.mel_filters(128))
+    ctx.load_weights(w)
+    ctx.set_tokens(st.sot, st.eot, st.task, st.lang, st.no_speech, st.no_timestamps, st.ts_zero, st.ts_one)
+    ctx.transcode_batch(np.stack([synth.synth_pcm_window(i) for i in range(B)]), want_output=False)
+    want = [st.sot, st.lang, st.task] + [plan[p] for p in range(2, 9)]
+    fused = ctx.decode(B, 0.0)
+    ctx.set_decode_mode(True)
+    separate = ctx.decode(B, 0.0)
+    for b in range(B):
+        assert fused[b]["tokens"] == want == separate[b]["tokens"], b
+        assert abs(fused[b]["avg_logprob"] - separate[b]["avg_logprob"]) < 5e-3
+    ctx.close()
+
+
 def test_fused_and_separate_decode_agree(lib):
     """The fused cooperative step kernel against the per-operation kernels (nb200_set_decode_mode) on three windows in lock-step:
     a planted, confident decoder gives identical tokens; a random-init decoder run to the stop rule (max_target_positions - 1: 28 launches
