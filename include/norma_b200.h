@@ -44,7 +44,8 @@ typedef enum {
     NB200_ARCH_MISMATCH = 6,
     NB200_IO_ERROR = 7,     /* whisper::Error::Io: a checkpoint file cannot be read */
     NB200_PARSE_ERROR = 8,  /* whisper::Error::{Json, LoadTokenizer} / candle's safetensors errors */
-    NB200_NOT_FOUND = 9     /* whisper::Error::TokenId: the tokenizer has no such token (src/models/whisper/mod.rs:86-90) */
+    NB200_NOT_FOUND = 9,    /* whisper::Error::TokenId: the tokenizer has no such token (src/models/whisper/mod.rs:86-90) */
+    NB200_BUFFER_TOO_SMALL = 10 /* a caller-allocated output buffer cannot hold the result; sizes are reported, nothing partial is written */
 } nb200_status;
 
 /* replaces candle_core::DType as returned by norma's `DType::to_dtype` (src/dtype.rs:15,23) */
@@ -139,10 +140,18 @@ NB200_API int nb200_run_resident(nb200_ctx *ctx, size_t n_windows, int do_mel, i
 NB200_API int nb200_fetch_features(nb200_ctx *ctx, size_t window, float *out, size_t n);
 NB200_API int nb200_fetch_mel(nb200_ctx *ctx, size_t window, float *out, size_t n);
 
+/* the `xa` / `audio_features` ARGUMENT of the reference's decoder calls (model.rs:279, 466): host [n_windows][1500][d_model] f32 become the
+ * resident audio features of windows [0, n_windows) without running the encoder (a maintainer who keeps candle's encoder, or a test that
+ * feeds the decoder directly) */
+NB200_API int nb200_set_audio_features(nb200_ctx *ctx, const float *xa, size_t n_windows);
+
 /* ---- seam (3): replaces `Type::decoder_forward(tokens, xa, flush)` -> candle `TextDecoder::forward`
  *      (model.rs:466-476).  tokens: ALL n tokens so far of window `window` (the reference keeps no
  *      self-attention cache); xa = that window's resident audio features; flush != 0 rebuilds the
- *      cross-attention K/V cache.  hidden_out (nullable): [n][d_model] f32. ------------------------------- */
+ *      cross-attention K/V cache.  hidden_out (nullable): [n][d_model] f32, all n positions.
+ *      Cost: the reference recomputes all n positions on every call (O(n^2) steps per window over norma's loop, model.rs:317-322).
+ *      Here a call with flush == 0 whose first k tokens are the tokens of the previous call on the same window runs only positions
+ *      [k, n) — one step per token when the five-method seam is bound literally — and returns the cached rows for [0, k). ---------- */
 NB200_API int nb200_decoder_forward(nb200_ctx *ctx, size_t window, const uint32_t *tokens, size_t n, int flush, float *hidden_out);
 /* ---- seam (4): replaces `Type::decoder_final_linear(x)` (model.rs:478-483): hidden [d] -> logits [vocab] */
 NB200_API int nb200_final_linear(nb200_ctx *ctx, const float *hidden, float *logits_out);
@@ -158,6 +167,16 @@ NB200_API int nb200_reset_kv_cache(nb200_ctx *ctx);
  *      tokens (bounded tests). ----------------------------------------------------------------------------- */
 NB200_API int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
                         double *avg_logprob, double *no_speech_prob);
+
+/* the same loop opened up (what the reference does per iteration of model.rs:317-371 is visible between the calls):
+ *   begin    prompt positions, no-speech probability, first sampled token (model.rs:285-315 and the first pass of the loop)
+ *   advance  up to n_steps more positions for all windows; *all_done (nullable) = 1 if every window had already finished (nothing ran)
+ *   peek     logits [vocab] of `window` at the last computed position = what `decoder_final_linear` returned there (model.rs:324-329)
+ *   end      the DecodingResults, as nb200_decode returns them.  nb200_decode == begin; advance(16) until done; end. */
+NB200_API int nb200_decode_begin(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens);
+NB200_API int nb200_decode_advance(nb200_ctx *ctx, size_t n_steps, int *all_done);
+NB200_API int nb200_decode_peek_logits(nb200_ctx *ctx, size_t window, float *logits_out);
+NB200_API int nb200_decode_end(nb200_ctx *ctx, uint32_t *tokens_out, size_t *n_tokens, double *avg_logprob, double *no_speech_prob);
 
 /* how the greedy steady state runs: NB200_DECODE_AUTO (default) = the fused cooperative step kernel when the context supports it (bf16),
  * NB200_DECODE_SEPARATE = the per-operation kernels replayed as a CUDA graph (always used for t > 0 and in F32 mode).  Same results up to the
@@ -186,9 +205,17 @@ NB200_API void nb200_model_destroy(nb200_model *m);
 NB200_API const char *nb200_model_last_error(nb200_model *m);
 NB200_API int nb200_model_set_vocab(nb200_model *m, uint32_t id, const char *bytes, size_t n);
 /* replaces `Model::transcribe(&mut self, data: &mut Vec<f32>, final_chunk) -> Result<String, _>` (model.rs:55-160).
- * text_out: NUL-terminated (truncated to text_cap); seg_out: [n_segments, len_0, tokens_0.., len_1, tokens_1.., ..] */
+ * text_out: NUL-terminated UTF-8; seg_out: [n_segments, len_0, tokens_0.., len_1, tokens_1.., ..].  *text_len (bytes, without the NUL)
+ * and *seg_len (words) always report the full sizes.  If a buffer is too small NOTHING partial is written and the call returns
+ * NB200_BUFFER_TOO_SMALL: the audio has been consumed, the result is kept and nb200_model_last_result delivers it into larger buffers.
+ * One deliberate divergence: a decoding result without a drainable segment (the silent window: prompt only, avg_logprob 0) makes the
+ * reference loop forever on the same slice (model.rs:68-150 never drains it); here the slice is dropped like the no-speech skip of
+ * model.rs:95-98 and counted in nb200_model_no_progress_windows. */
 NB200_API int nb200_model_transcribe(nb200_model *m, const float *data, size_t n, int final_chunk, char *text_out, size_t text_cap,
                                      size_t *text_len, uint32_t *seg_out, size_t seg_cap, size_t *seg_len);
+NB200_API int nb200_model_last_result(nb200_model *m, char *text_out, size_t text_cap, size_t *text_len, uint32_t *seg_out, size_t seg_cap,
+                                      size_t *seg_len);
+NB200_API int nb200_model_no_progress_windows(nb200_model *m, size_t *n);
 NB200_API int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_encodes, size_t *n_decodes, size_t *n_resets);
 NB200_API int nb200_model_script_push(nb200_model *m, double avg_logprob, double no_speech_prob, const uint32_t *tokens, size_t n);
 NB200_API int nb200_model_script_log(nb200_model *m, size_t i, size_t *encode_len, double *decode_temp);

@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -10,6 +11,11 @@
 
 static thread_local std::string g_err;
 int decoder_logits_rows(nb200_ctx *ctx, int n);
+static void destroy_step_graphs(nb200_ctx *ctx) {
+    for (auto &g : ctx->step_graphs) cudaGraphExecDestroy(g.second);
+    ctx->step_graphs.clear();
+    ctx->run.gexec = nullptr;
+}
 
 int nb200_fail(nb200_ctx *ctx, int code, const char *fmt, ...) {
     char buf[1024];
@@ -242,18 +248,12 @@ int check_ready(nb200_ctx *ctx, bool need_weights, bool need_filters) {
 // ---------------------------------------------------------------------------------------------------------
 // encoder: candle `AudioEncoder::forward` on windows [0, B)
 // ---------------------------------------------------------------------------------------------------------
-static int g_attn_impl = -1;  // -1 unset, 0 simt, 1 tcgen05
-
 int encoder_run(nb200_ctx *ctx, int B) {
     const nb200_config &c = ctx->cfg;
     const int d = c.d_model, T = c.max_source_positions, n_mel = c.num_mel_bins, H = c.encoder_attention_heads;
     const bool bf = ctx->compute == NB200_BF16;
     const int M = B * T;
     const float qk_scale = powf((float)HEAD_DIM, -0.25f);
-    if (g_attn_impl < 0) {
-        const char *e = getenv("NB200_ATTN");
-        g_attn_impl = (e && !strcmp(e, "simt")) ? 0 : 1;  // NB200_ATTN=simt selects the CUDA-core kernel (debug)
-    }
     auto gemm = [&](const void *A, const void *W, const GemmShape &s, const Epilogue &e) {
         return bf ? launch_gemm_bf16(ctx, (const bf16 *)A, (const bf16 *)W, s, e) : launch_gemm_f32(ctx, (const float *)A, (const float *)W, s, e);
     };
@@ -286,7 +286,7 @@ int encoder_run(nb200_ctx *ctx, int B) {
             e.out = ctx->qkv; e.ldo = 3 * d; e.out_bf16 = bf;
             NB_TRY(gemm(ctx->h, w.wqkv, s, e));
         }
-        if (bf && g_attn_impl == 1) NB_TRY(launch_attention_tc(ctx, (const bf16 *)ctx->qkv, (bf16 *)ctx->attn, B, T, H));
+        if (bf && ctx->opt.attn_tc) NB_TRY(launch_attention_tc(ctx, (const bf16 *)ctx->qkv, (bf16 *)ctx->attn, B, T, H));
         else NB_TRY(launch_attention_simt(ctx, ctx->qkv, ctx->attn, B, T, H, bf));
         {
             GemmShape s{M, 1, d, d, d, (long long)M * d};
@@ -316,6 +316,65 @@ int encoder_run(nb200_ctx *ctx, int B) {
     else NB_TRY(launch_layernorm(ctx, ctx->x, ctx->lnpost_g, ctx->lnpost_b, M, d, ctx->enc_out, 0, nullptr));
     ctx->n_resident = B;
     ctx->cross_valid = false;
+    ctx->seam_window = -1;
+    return NB200_OK;
+}
+
+// log-mel and / or encoder over windows [0, B) replayed as ONE CUDA graph per (B, stages, buffer slot).  A 32-layer encoder is ~200
+// launches: at one window per call (BASELINE configs 2 and 4) issuing them one by one costs more host time than the kernels take.  The
+// tensor maps are encoded once, at capture.  Profiling runs (per-kernel events) and NB200_ENCODER_NOGRAPH launch kernel by kernel.
+int run_front(nb200_ctx *ctx, int B, bool do_mel, bool do_enc, int slot) {
+    auto direct = [&]() -> int {
+        if (do_mel) {
+            NB_TRY(launch_mel(ctx, B));
+            NB_TRY(launch_mel_norm(ctx, B));
+        }
+        if (do_enc) NB_TRY(encoder_run(ctx, B));
+        return NB200_OK;
+    };
+    if (ctx->profiling || !ctx->opt.encoder_graph) return direct();
+    const long long key = ((long long)B << 8) | (do_mel ? 1 : 0) | (do_enc ? 2 : 0) | ((long long)slot << 2);
+    auto it = ctx->front_graphs.find(key);
+    if (it == ctx->front_graphs.end()) {
+        CapturedGraph cg;
+        const int64_t l0 = ctx->launches;
+        int64_t c0[NB200_K_COUNT];
+        for (int i = 0; i < NB200_K_COUNT; ++i) c0[i] = ctx->prof_launches[i];
+        const double f0 = ctx->prof_gemm_flops;
+        const int res0 = ctx->n_resident;
+        const bool cv0 = ctx->cross_valid;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int st = direct();
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        cg.launches = ctx->launches - l0;  // nothing ran yet: the counters describe the graph, every replay adds them
+        ctx->launches = l0;
+        for (int i = 0; i < NB200_K_COUNT; ++i) {
+            cg.by_class[i] = ctx->prof_launches[i] - c0[i];
+            ctx->prof_launches[i] = c0[i];
+        }
+        ctx->prof_gemm_flops = f0;
+        ctx->n_resident = res0;
+        ctx->cross_valid = cv0;
+        if (st != NB200_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (st != NB200_OK) return st;
+            return nb200_fail(ctx, NB200_CUDA_ERROR, "front graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&cg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "front graph instantiate failed: %s", cudaGetErrorString(ie));
+        it = ctx->front_graphs.emplace(key, cg).first;
+    }
+    CUDA_TRY(ctx, cudaGraphLaunch(it->second.exec, ctx->stream));
+    ctx->launches += it->second.launches;
+    for (int i = 0; i < NB200_K_COUNT; ++i) ctx->prof_launches[i] += it->second.by_class[i];
+    if (do_enc) {
+        ctx->n_resident = B;
+        ctx->cross_valid = false;
+        ctx->seam_window = -1;
+    }
     return NB200_OK;
 }
 
@@ -367,6 +426,21 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
     ctx->cfg = c;
     ctx->compute = compute;
     ctx->sm_count = prop.multiProcessorCount;
+    {   // A/B and debug switches: read once, here, into the context
+        auto env = [](const char *k) { return getenv(k); };
+        auto is = [&](const char *k, const char *v) { const char *e = env(k); return e && !strcmp(e, v); };
+        CtxOptions &o = ctx->opt;
+        o.gemm_mode = is("NB200_GEMM", "1cta") ? 1 : is("NB200_GEMM", "1cta128") ? 3 : 2;
+        o.gemm_epi_tma = is("NB200_EPI", "direct") ? 0 : 1;
+        o.gemm_nofit = env("NB200_GEMM_NOFIT") != nullptr;
+        o.gemm_debug = env("NB200_GEMM_DEBUG") ? atoi(env("NB200_GEMM_DEBUG")) : 0;
+        o.attn_tc = is("NB200_ATTN", "simt") ? 0 : 1;
+        o.decode_fused = (env("NB200_DECODE_FUSED") && env("NB200_DECODE_FUSED")[0] == '0') ? 0 : 1;
+        o.decode_graph = env("NB200_DECODE_NOGRAPH") ? 0 : 1;
+        o.encoder_graph = env("NB200_ENCODER_NOGRAPH") ? 0 : 1;
+        o.ln_fused = (env("NB200_LN_FUSED") && env("NB200_LN_FUSED")[0] == '0') ? 0 : 1;
+        o.prof_dump = env("NB200_PROF_DUMP") != nullptr;
+    }
     int st = [&]() -> int {
         NB_TRY(set_device(ctx));
         CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -418,6 +492,7 @@ void nb200_destroy(nb200_ctx *ctx) {
     cudaSetDevice(ctx->ordinal);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &g : ctx->step_graphs) cudaGraphExecDestroy(g.second);
+    for (auto &g : ctx->front_graphs) cudaGraphExecDestroy(g.second.exec);
     for (void *p : ctx->allocs) cudaFree(p);
     for (auto &r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -595,6 +670,7 @@ int nb200_set_tokens(nb200_ctx *ctx, const nb200_special_tokens *tok) {
         return nb200_fail(ctx, NB200_INVALID_ARG, "set_tokens: token id out of range for vocab %u", V);
     ctx->tok = *tok;
     ctx->has_tokens = true;
+    destroy_step_graphs(ctx);  // the captured select kernels hold the token ids by value
     return upload_suppress(ctx);
 }
 
@@ -663,7 +739,7 @@ int nb200_encoder_forward(nb200_ctx *ctx, const float *mel, size_t n_windows, fl
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->mel_norm, mel, n_windows * ctx->cfg.num_mel_bins * N_FRAMES * 4, cudaMemcpyHostToDevice, ctx->stream));
         NB_TRY(launch_mel_from_host_layout(ctx, (int)n_windows));
     }
-    NB_TRY(encoder_run(ctx, (int)n_windows));
+    NB_TRY(run_front(ctx, (int)n_windows, false, true, 0));
     if (out)
         CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out, n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -674,9 +750,7 @@ int nb200_encoder_forward(nb200_ctx *ctx, const float *mel, size_t n_windows, fl
 int nb200_transcode_batch(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t stride, const size_t *lens, float *out) {
     NB_TRY(check_ready(ctx, true, true));
     NB_TRY(stage_pcm(ctx, pcm, n_windows, stride, lens));
-    NB_TRY(launch_mel(ctx, (int)n_windows));
-    NB_TRY(launch_mel_norm(ctx, (int)n_windows));
-    NB_TRY(encoder_run(ctx, (int)n_windows));
+    NB_TRY(run_front(ctx, (int)n_windows, true, true, 0));
     if (out)
         CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->enc_out, n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
                                       ctx->stream));
@@ -736,12 +810,8 @@ int nb200_transcode_submit(nb200_ctx *ctx, const float *pcm, size_t n_windows, s
     ctx->pcm_len = ctx->pipe_len[s];
     ctx->enc_out = ctx->pipe_out[s];
     if (ctx->compute == NB200_F32) ctx->enc_out_c = ctx->enc_out;
-    int st = launch_mel(ctx, (int)n_windows);
-    if (st == NB200_OK) {
-        cudaEventRecord(ctx->ev_mel[s], ctx->stream);
-        st = launch_mel_norm(ctx, (int)n_windows);
-    }
-    if (st == NB200_OK) st = encoder_run(ctx, (int)n_windows);
+    int st = run_front(ctx, (int)n_windows, true, true, s);
+    if (st == NB200_OK) cudaEventRecord(ctx->ev_mel[s], ctx->stream);  // this slot's PCM has been consumed (its next upload is two submits away)
     ctx->pcm = save_pcm;
     ctx->pcm_len = save_len;
     ctx->enc_out = save_out;
@@ -775,11 +845,7 @@ int nb200_stage_pcm(nb200_ctx *ctx, const float *pcm, size_t n_windows, size_t s
 int nb200_run_resident(nb200_ctx *ctx, size_t n_windows, int do_mel, int do_encoder) {
     NB_TRY(check_ready(ctx, do_encoder != 0, do_mel != 0));
     if (n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch) return nb200_fail(ctx, NB200_INVALID_ARG, "run_resident: n_windows=%zu", n_windows);
-    if (do_mel) {
-        NB_TRY(launch_mel(ctx, (int)n_windows));
-        NB_TRY(launch_mel_norm(ctx, (int)n_windows));
-    }
-    if (do_encoder) NB_TRY(encoder_run(ctx, (int)n_windows));
+    NB_TRY(run_front(ctx, (int)n_windows, do_mel != 0, do_encoder != 0, 0));
     return NB200_OK;  // asynchronous on the ctx stream: pair with nb200_timer_stop / nb200_sync
 }
 
@@ -807,6 +873,22 @@ static int check_decoder(nb200_ctx *ctx) {
     return NB200_OK;
 }
 
+// `audio_features` as an argument (model.rs:279, 466: decode / decoder_forward take `xa`): host [n_windows][1500][d_model] f32 become the
+// resident features of windows [0, n_windows), as if the encoder had produced them
+int nb200_set_audio_features(nb200_ctx *ctx, const float *xa, size_t n_windows) {
+    NB_TRY(check_ready(ctx, true, false));
+    if (!xa || n_windows == 0 || n_windows > (size_t)ctx->cfg.max_batch)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "set_audio_features: n_windows=%zu (max_batch %d)", n_windows, ctx->cfg.max_batch);
+    const size_t n = n_windows * ctx->cfg.max_source_positions * ctx->cfg.d_model;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->enc_out, xa, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->compute == NB200_BF16) NB_TRY(launch_f32_to_bf16(ctx, ctx->enc_out, (bf16 *)ctx->enc_out_c, n));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_resident = (int)n_windows;
+    ctx->cross_valid = false;
+    ctx->seam_window = -1;
+    return NB200_OK;
+}
+
 int nb200_decoder_forward(nb200_ctx *ctx, size_t window, const uint32_t *tokens, size_t n, int flush, float *hidden_out) {
     NB_TRY(check_decoder(ctx));
     const nb200_config &c = ctx->cfg;
@@ -815,30 +897,34 @@ int nb200_decoder_forward(nb200_ctx *ctx, size_t window, const uint32_t *tokens,
     if ((int)window >= ctx->n_resident) return nb200_fail(ctx, NB200_NOT_LOADED, "decoder_forward: window %zu has no resident audio features", window);
     for (size_t i = 0; i < n; ++i)
         if (tokens[i] >= (uint32_t)c.vocab_size) return nb200_fail(ctx, NB200_INVALID_ARG, "decoder_forward: token %u out of vocab", tokens[i]);
-    if (flush || !ctx->cross_valid) NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
     const int P = c.max_target_positions, d = c.d_model;
+    const bool rebuild = flush || !ctx->cross_valid;
+    if (rebuild) {
+        NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
+        ctx->seam_window = -1;
+    }
+    if (ctx->run.active) ctx->run.active = false;  // a decode in progress shares the self-attention cache: it is abandoned
+    if (!ctx->seam_hidden) NB_TRY(dev_alloc_t(ctx, (size_t)P * d, &ctx->seam_hidden));
+    // The reference recomputes every position on every call (candle keeps no self-attention cache), so norma's loop costs O(n^2) steps per
+    // window.  Here the self-attention K/V rows and the hidden rows of the positions computed by the previous call are still valid when
+    // this call extends the same token prefix with the same cross K/V (flush = 0): only the new positions run.
+    size_t first = 0;
+    if (ctx->seam_window == (int)window && ctx->seam_tokens.size() <= n && std::equal(ctx->seam_tokens.begin(), ctx->seam_tokens.end(), tokens))
+        first = ctx->seam_tokens.size();
+    ctx->seam_window = -1;  // until this call has completed
     int ln = (int)n;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tokens + window * P, tokens, n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_len + window, &ln, 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // `tokens` and `ln` are consumed
+    for (size_t pos = first; pos < n; ++pos) {
+        NB_TRY(decoder_step(ctx, (int)window, 1, (int)pos, 0));
+        NB_TRY(decoder_copy_hidden(ctx, ctx->seam_hidden + pos * d, d));
+    }
+    if (hidden_out) CUDA_TRY(ctx, cudaMemcpyAsync(hidden_out, ctx->seam_hidden, n * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    // hidden states are gathered in ctx->dff-sized scratch? no: reuse logits buffer (>= 448*d floats only if V >= ..) -> dedicated rows of dhid
-    float *hid_all = nullptr;
-    if (hidden_out) {
-        CUDA_TRY(ctx, cudaMalloc(&hid_all, n * d * 4));
-    }
-    int st = NB200_OK;
-    for (size_t pos = 0; pos < n && st == NB200_OK; ++pos) {
-        st = decoder_step(ctx, (int)window, 1, (int)pos, 0);
-        if (st == NB200_OK && hid_all) st = decoder_copy_hidden(ctx, hid_all + pos * d, d);
-    }
-    if (st == NB200_OK && hid_all) {
-        cudaError_t e = cudaMemcpyAsync(hidden_out, hid_all, n * d * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e != cudaSuccess) st = nb200_fail(ctx, NB200_CUDA_ERROR, "decoder_forward D2H: %s", cudaGetErrorString(e));
-    }
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    if (hid_all) cudaFree(hid_all);
-    if (st == NB200_OK && e2 != cudaSuccess) st = nb200_fail(ctx, NB200_CUDA_ERROR, "decoder_forward: %s", cudaGetErrorString(e2));
-    return st;
+    ctx->seam_window = (int)window;
+    ctx->seam_tokens.assign(tokens, tokens + n);
+    return NB200_OK;
 }
 
 int nb200_final_linear(nb200_ctx *ctx, const float *hidden, float *logits_out) {
@@ -867,6 +953,8 @@ int nb200_detect_language(nb200_ctx *ctx, size_t window, const uint32_t *lang_to
         if (lang_tokens[i] >= (uint32_t)c.vocab_size) return nb200_fail(ctx, NB200_INVALID_ARG, "detect_language: token %u out of vocab", lang_tokens[i]);
     // `decoder_forward([[sot]], audio_features, flush = true)` then `final_linear(ys[..1])` (model.rs:195-197)
     NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
+    ctx->seam_window = -1;
+    ctx->run.active = false;
     const int P = c.max_target_positions;
     const int one = 1;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_tokens + window * P, &ctx->tok.sot, 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -903,15 +991,45 @@ int nb200_decode_greedy(nb200_ctx *ctx, size_t n_windows, size_t max_new_tokens,
     return nb200_decode(ctx, n_windows, 0.0f, 0, max_new_tokens, tokens_out, n_tokens, avg_logprob, no_speech_prob);
 }
 
-int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
-                 double *avg_logprob, double *no_speech_prob) {
+// ---- norma's `Model::decode` (model.rs:279-390) opened up into begin / advance / end so that a caller (and the parity tests) can look at
+// every step's logits, exactly what `decoder_final_linear` returns inside the reference loop (model.rs:324-329) --------------------------
+static int ensure_step_graph(nb200_ctx *ctx) {
+    nb200_ctx::DecodeRun &r = ctx->run;
+    if (r.gexec || ctx->profiling || !ctx->opt.decode_graph) return NB200_OK;
+    const int gkey = r.B * 2 + r.greedy;
+    auto it = ctx->step_graphs.find(gkey);
+    if (it != ctx->step_graphs.end()) { r.gexec = it->second; return NB200_OK; }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int st = decoder_step(ctx, 0, r.B, -1, 1);
+    if (st == NB200_OK) st = decoder_select(ctx, r.B, r.greedy);
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (st != NB200_OK || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (st != NB200_OK) return st;
+        return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph capture failed: %s", cudaGetErrorString(ce));
+    }
+    cudaGraphExec_t gexec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph instantiate failed: %s", cudaGetErrorString(ie));
+    ctx->step_graphs[gkey] = gexec;
+    r.gexec = gexec;
+    return NB200_OK;
+}
+
+int nb200_decode_begin(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens) {
     NB_TRY(check_decoder(ctx));
     if (!(temperature >= 0.0f)) return nb200_fail(ctx, NB200_INVALID_ARG, "decode: temperature must be >= 0");
     const nb200_config &c = ctx->cfg;
     if (!ctx->has_tokens) return nb200_fail(ctx, NB200_NOT_LOADED, "special tokens not set (call nb200_set_tokens)");
-    if (n_windows == 0 || (int)n_windows > ctx->n_resident || !tokens_out || !n_tokens)
-        return nb200_fail(ctx, NB200_INVALID_ARG, "decode_greedy: n_windows=%zu but %d windows have resident audio features", n_windows, ctx->n_resident);
-    const int B = (int)n_windows, P = c.max_target_positions;
+    if (n_windows == 0 || (int)n_windows > ctx->n_resident)
+        return nb200_fail(ctx, NB200_INVALID_ARG, "decode: n_windows=%zu but %d windows have resident audio features", n_windows, ctx->n_resident);
+    nb200_ctx::DecodeRun &r = ctx->run;
+    r = nb200_ctx::DecodeRun{};
+    ctx->seam_window = -1;  // the self-attention caches are about to be overwritten
+    const int B = (int)n_windows;
     const int plen = ctx->tok.lang != UINT32_MAX ? 3 : 2;
     // `decoder_forward(prompt, audio_features, flush = true)` (model.rs:297-299): rebuild the cross K/V cache
     NB_TRY(decoder_build_cross_kv(ctx, ctx->n_resident));
@@ -921,67 +1039,88 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
         NB_TRY(decoder_step(ctx, 0, B, pos, pos == 0 || pos == plen - 1));
         if (pos == 0) NB_TRY(decoder_nospeech(ctx, B));
     }
-    const int greedy = temperature == 0.0f ? 1 : 0;
-    NB_TRY(decoder_select(ctx, B, greedy));  // first sampled token; advances the device position to plen
-    // Steady state: one decode step (embed .. 2 x attention .. MLP .. logits .. select) is a CUDA graph replayed with the
-    // position living on the device; the host only polls the done flags every POLL steps (no per-token sync or transfer).
+    r.greedy = temperature == 0.0f ? 1 : 0;
+    NB_TRY(decoder_select(ctx, B, r.greedy));  // first sampled token; advances the device position to plen
+    r.B = B;
+    r.plen = plen;
+    r.pos = plen;
+    // greedy steady state: up to 16 steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 or
+    // nb200_set_decode_mode fall back to the ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose
+    // sampler is a single-block kernel, and for F32 contexts)
+    r.use_fused = r.greedy && ctx->opt.decode_fused && !ctx->decode_separate && !ctx->fused_failed && decoder_fused_supported(ctx) &&
+                  B <= decoder_fused_max_windows() && (int)c.max_target_positions >= plen;
+    if (r.use_fused && decoder_fused_prepare(ctx) != NB200_OK) r.use_fused = false;
+    if (!r.use_fused) NB_TRY(ensure_step_graph(ctx));
+    r.active = true;
+    return NB200_OK;
+}
+
+// up to n_steps more positions for every window of the run (model.rs:317-371; the position, temperature and token budget live on the
+// device).  The done flags are read back first: *all_done = 1 means every window had already finished and nothing was launched.
+int nb200_decode_advance(nb200_ctx *ctx, size_t n_steps, int *all_done) {
+    NB_TRY(check_decoder(ctx));
+    nb200_ctx::DecodeRun &r = ctx->run;
+    if (!r.active) return nb200_fail(ctx, NB200_INVALID_ARG, "decode_advance: no decode in progress (call nb200_decode_begin)");
+    const int B = r.B, P = ctx->cfg.max_target_positions;
     std::vector<int> done(B);
-    // greedy steady state: POLL steps (embed .. logits .. select each) are one cooperative kernel; NB200_DECODE_FUSED=0 falls back to the
-    // ~25 separate kernels per step replayed as a CUDA graph (the only path for t > 0, whose sampler is a single-block kernel)
-    static const bool fused_ok = [] { const char *e = getenv("NB200_DECODE_FUSED"); return !(e && e[0] == '0'); }();
-    bool use_fused = greedy && fused_ok && !ctx->decode_separate && !ctx->fused_failed && decoder_fused_supported(ctx) && B <= decoder_fused_max_windows();
-    const bool graph_ok = !ctx->profiling && getenv("NB200_DECODE_NOGRAPH") == nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    auto ensure_graph = [&]() -> int {
-        if (gexec || !graph_ok) return NB200_OK;
-        const int gkey = B * 2 + greedy;
-        auto it = ctx->step_graphs.find(gkey);
-        if (it != ctx->step_graphs.end()) { gexec = it->second; return NB200_OK; }
-        cudaGraph_t graph = nullptr;
-        CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int st = decoder_step(ctx, 0, B, -1, 1);
-        if (st == NB200_OK) st = decoder_select(ctx, B, greedy);
-        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
-        if (st != NB200_OK) return st;
-        if (ce != cudaSuccess) return nb200_fail(ctx, NB200_CUDA_ERROR, "decode graph capture failed: %s", cudaGetErrorString(ce));
-        CUDA_TRY(ctx, cudaGraphInstantiate(&gexec, graph, 0));
-        cudaGraphDestroy(graph);
-        ctx->step_graphs[gkey] = gexec;
-        return NB200_OK;
-    };
-    const int POLL = 16;
-    if (use_fused && decoder_fused_prepare(ctx) != NB200_OK) use_fused = false;
-    if (!use_fused) NB_TRY(ensure_graph());
-    for (int pos = plen; pos < P;) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        bool all = true;
+    CUDA_TRY(ctx, cudaMemcpyAsync(done.data(), ctx->d_done, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    bool all = r.pos >= P;
+    if (!all) {
+        all = true;
         for (int b = 0; b < B; ++b) all &= done[b] != 0;
-        if (all) break;
-        const int n = (graph_ok || use_fused) ? std::min(POLL, P - pos) : 1;
-        if (use_fused) {  // one cooperative launch for the next n positions: the CTAs stay resident between steps
+    }
+    if (all_done) *all_done = all ? 1 : 0;
+    if (all || n_steps == 0) return NB200_OK;
+    int left = (int)std::min<size_t>(n_steps, (size_t)(P - r.pos));
+    const bool batchable = r.use_fused || r.gexec != nullptr;
+    while (left > 0) {
+        const int n = batchable ? std::min(left, 16) : 1;
+        if (r.use_fused) {  // one cooperative launch for the next n positions: the CTAs stay resident between steps
             if (decoder_step_fused(ctx, B, n) == NB200_OK) {
-                pos += n;
+                r.pos += n;
+                left -= n;
                 continue;
             }
             // the cooperative launch was refused (e.g. the SMs are shared with another process and 148 CTAs cannot be co-resident):
             // nothing ran, the decoding state is untouched; this context uses the separate kernels from now on
             cudaGetLastError();
             ctx->fused_failed = true;
-            use_fused = false;
-            NB_TRY(ensure_graph());
+            r.use_fused = false;
+            NB_TRY(ensure_step_graph(ctx));
         }
         for (int i = 0; i < n; ++i) {
-            if (gexec) CUDA_TRY(ctx, cudaGraphLaunch(gexec, ctx->stream));
+            if (r.gexec) CUDA_TRY(ctx, cudaGraphLaunch(r.gexec, ctx->stream));
             else {
                 NB_TRY(decoder_step(ctx, 0, B, -1, 1));
-                NB_TRY(decoder_select(ctx, B, greedy));
+                NB_TRY(decoder_select(ctx, B, r.greedy));
             }
         }
-        pos += n;
+        r.pos += n;
+        left -= n;
     }
+    return NB200_OK;
+}
+
+// logits [vocab] of `window` at the LAST computed position: after nb200_decode_begin the ones the first sampled token was chosen from,
+// after k single-step advances the ones of sampled token k + 1 (what `decoder_final_linear` returned there, model.rs:324-329)
+int nb200_decode_peek_logits(nb200_ctx *ctx, size_t window, float *logits_out) {
+    NB_TRY(check_decoder(ctx));
+    if (!ctx->run.active || (int)window >= ctx->run.B || !logits_out) return nb200_fail(ctx, NB200_INVALID_ARG, "decode_peek_logits: bad argument or no decode in progress");
+    const size_t V = ctx->cfg.vocab_size;
+    CUDA_TRY(ctx, cudaMemcpyAsync(logits_out, ctx->logits + window * V, V * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_decode_end(nb200_ctx *ctx, uint32_t *tokens_out, size_t *n_tokens, double *avg_logprob, double *no_speech_prob) {
+    NB_TRY(check_decoder(ctx));
+    nb200_ctx::DecodeRun &r = ctx->run;
+    if (!r.active || !tokens_out || !n_tokens) return nb200_fail(ctx, NB200_INVALID_ARG, "decode_end: bad argument or no decode in progress");
+    const int B = r.B, P = ctx->cfg.max_target_positions, plen = r.plen;
+    r.active = false;
     std::vector<uint32_t> toks((size_t)B * P);
-    std::vector<int> len(B);
+    std::vector<int> len(B), done(B);
     std::vector<double> slp(B);
     std::vector<float> nsp(B);
     CUDA_TRY(ctx, cudaMemcpyAsync(toks.data(), ctx->d_tokens, toks.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1012,6 +1151,20 @@ int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t s
         if (no_speech_prob) no_speech_prob[b] = (double)nsp[b];
     }
     return NB200_OK;
+}
+
+int nb200_decode(nb200_ctx *ctx, size_t n_windows, float temperature, uint64_t seed, size_t max_new_tokens, uint32_t *tokens_out, size_t *n_tokens,
+                 double *avg_logprob, double *no_speech_prob) {
+    if (!tokens_out || !n_tokens) return nb200_fail(ctx, NB200_INVALID_ARG, "decode: NULL output");
+    NB_TRY(nb200_decode_begin(ctx, n_windows, temperature, seed, max_new_tokens));
+    // the host only polls the done flags every 16 steps (no per-token sync or transfer)
+    for (;;) {
+        int all = 0;
+        const int st = nb200_decode_advance(ctx, 16, &all);
+        if (st != NB200_OK) { ctx->run.active = false; return st; }
+        if (all) break;
+    }
+    return nb200_decode_end(ctx, tokens_out, n_tokens, avg_logprob, no_speech_prob);
 }
 
 // ---- streaming front half (BASELINE config 4): the window-0 PCM lives on the device, small chunks are
@@ -1064,7 +1217,7 @@ int nb200_stream_features(nb200_ctx *ctx, int run_encoder, float *mel_out, float
     NB_TRY(launch_mel_norm(ctx, 1));
     if (mel_out) CUDA_TRY(ctx, cudaMemcpyAsync(mel_out, ctx->mel_norm, (size_t)ctx->cfg.num_mel_bins * N_FRAMES * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (run_encoder) {
-        NB_TRY(encoder_run(ctx, 1));
+        NB_TRY(run_front(ctx, 1, false, true, 0));
         if (features_out)
             CUDA_TRY(ctx, cudaMemcpyAsync(features_out, ctx->enc_out, (size_t)ctx->cfg.max_source_positions * ctx->cfg.d_model * 4, cudaMemcpyDeviceToHost,
                                           ctx->stream));
@@ -1118,7 +1271,7 @@ int nb200_profile_read(nb200_ctx *ctx, float *ms_by_class, int64_t *launches_by_
         if (launches_by_class) launches_by_class[i] = ctx->prof_launches[i];
     }
     if (flops_gemm) *flops_gemm = ctx->prof_gemm_flops;
-    if (getenv("NB200_PROF_DUMP")) {
+    if (ctx->opt.prof_dump) {
         for (auto &kv : ctx->prof_by_tag)
             fprintf(stderr, "[nb200 prof] class %lld tag %lld: %.3f ms over %lld launches (%.1f us each)\n", kv.first / 1000000000000LL,
                     kv.first % 1000000000000LL, kv.second.first, kv.second.second, 1e3 * kv.second.first / (double)kv.second.second);
@@ -1249,8 +1402,7 @@ int nb200_test_attention(nb200_ctx *ctx, const float *qkv, int B, int T, int n_h
             CUDA_TRY(ctx, cudaMalloc(&dq16, nq * 2));
             CUDA_TRY(ctx, cudaMalloc(&do16, no * 2));
             NB_TRY(launch_f32_to_bf16(ctx, dq32, dq16, nq));
-            const char *e = getenv("NB200_ATTN");
-            if (e && !strcmp(e, "simt")) NB_TRY(launch_attention_simt(ctx, dq16, do16, B, T, n_heads, 1));
+            if (!ctx->opt.attn_tc) NB_TRY(launch_attention_simt(ctx, dq16, do16, B, T, n_heads, 1));
             else NB_TRY(launch_attention_tc(ctx, dq16, do16, B, T, n_heads));
             std::vector<uint16_t> h(no);
             CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), do16, no * 2, cudaMemcpyDeviceToHost, ctx->stream));

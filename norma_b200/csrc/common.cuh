@@ -64,8 +64,31 @@ struct HostTensor {
     std::vector<int64_t> shape;
 };
 
+// debug / A-B switches, read from the environment ONCE per context at nb200_create (no process-wide mutable state on the launch path:
+// different contexts are driven from different threads, include/norma_b200.h "Conventions")
+struct CtxOptions {
+    int gemm_mode = 2;        // NB200_GEMM: 2 = CTA-pair 256 x 256 tiles (default), 1 = "1cta", 3 = "1cta128"
+    int gemm_epi_tma = 1;     // NB200_EPI=direct -> 0: thread-per-row stores
+    int gemm_nofit = 0;       // NB200_GEMM_NOFIT: keep the pair tile for one window's worth of rows
+    int gemm_debug = 0;       // NB200_GEMM_DEBUG: microbenchmark switches of gemm_tc_kernel
+    int attn_tc = 1;          // NB200_ATTN=simt -> 0: CUDA-core attention
+    int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels
+    int decode_graph = 1;     // NB200_DECODE_NOGRAPH -> 0
+    int encoder_graph = 1;    // NB200_ENCODER_NOGRAPH -> 0: launch the encoder kernel by kernel
+    int ln_fused = 1;         // NB200_LN_FUSED=0 -> standalone LayerNorm kernels in the encoder
+    int prof_dump = 0;        // NB200_PROF_DUMP
+};
+
+// a captured launch sequence and what it stands for in the context's counters
+struct CapturedGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;                     // kernels in the graph (ctx->launches is advanced by this on every replay)
+    int64_t by_class[NB200_K_COUNT] = {0};
+};
+
 struct nb200_ctx {
     int ordinal = 0;
+    CtxOptions opt;
     nb200_config cfg{};
     nb200_dtype compute = NB200_BF16;
     cudaStream_t stream = nullptr;
@@ -150,6 +173,13 @@ struct nb200_ctx {
     float *d_attn_ws = nullptr;  // split-K decode attention partials [max_batch][heads][8][66]
     void *d_dyn = nullptr;  // DecodeDyn (decoder.cu): device-resident position / temperature / seed / token budget
     std::map<int, cudaGraphExec_t> step_graphs;  // captured decode step (embed .. logits .. select) per batch size
+    std::map<long long, CapturedGraph> front_graphs;  // captured log-mel / encoder passes per (windows, stages, buffer slot)
+    // decode in progress (nb200_decode_begin .. _end)
+    struct DecodeRun { bool active = false; int B = 0, plen = 0, pos = 0, greedy = 1; bool use_fused = false; cudaGraphExec_t gexec = nullptr; } run;
+    // seam (3) incremental state: the window whose self-attention K/V cache and hidden rows cover `seam_tokens`
+    int seam_window = -1;
+    std::vector<uint32_t> seam_tokens;
+    float *seam_hidden = nullptr;  // [max_target_positions][d] f32, allocated on first use
     float *suppress = nullptr;  // [V] additive mask (0 / -inf): Config::suppress_tokens U {no_timestamps}
     nb200_special_tokens tok{};
     std::vector<uint32_t> suppress_ids;

@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 namespace {
 
 constexpr int BM = 128, BK = 64;
@@ -416,18 +418,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_tmapEncodeTiled g_encode = nullptr;
-
-int tmap_encode(nb200_ctx *ctx, CUtensorMap *out, CUtensorMapDataType dt, const void *base, int rank, const uint64_t *dims,
-                const uint64_t *strides_bytes, const uint32_t *box) {
-    if (!g_encode) {
+// the driver entry point is resolved once per process, thread-safely (contexts are created and driven from different threads)
+PFN_tmapEncodeTiled tmap_encode_fn() {
+    static std::once_flag once;
+    static PFN_tmapEncodeTiled fn_ = nullptr;
+    std::call_once(once, [] {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
-            return nb200_fail(ctx, NB200_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
-        g_encode = (PFN_tmapEncodeTiled)fn;
-    }
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) fn_ = (PFN_tmapEncodeTiled)fn;
+    });
+    return fn_;
+}
+
+int tmap_encode(nb200_ctx *ctx, CUtensorMap *out, CUtensorMapDataType dt, const void *base, int rank, const uint64_t *dims,
+                const uint64_t *strides_bytes, const uint32_t *box) {
+    const PFN_tmapEncodeTiled g_encode = tmap_encode_fn();
+    if (!g_encode) return nb200_fail(ctx, NB200_CUDA_ERROR, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t gdim[5], gstr[5];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) {
@@ -482,19 +489,13 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     if (s.lda % 8 != 0 || s.a_bs % 8 != 0 || s.K % 8 != 0 || ((uintptr_t)A & 15) || ((uintptr_t)W & 15))
         return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "gemm_bf16: operands must be 16-byte aligned (K=%d lda=%lld a_bs=%lld)", s.K, s.lda,
                           s.a_bs);
-    static int mode = -1, epi = -1;  // NB200_GEMM=1cta: single-CTA kernel; NB200_EPI=direct: thread-per-row stores (A/B comparison)
-    if (mode < 0) {
-        const char *ev = getenv("NB200_GEMM");
-        mode = (ev && !strcmp(ev, "1cta")) ? 1 : (ev && !strcmp(ev, "1cta128")) ? 3 : 2;
-        ev = getenv("NB200_EPI");
-        epi = (ev && !strcmp(ev, "direct")) ? 0 : 1;
-    }
+    const int mode = ctx->opt.gemm_mode, epi = ctx->opt.gemm_epi_tma;  // NB200_GEMM / NB200_EPI, read at nb200_create (A/B comparison)
     // Tile configuration: the CTA-pair 256 x 256 tile wins everywhere except for ONE window's worth of rows (streaming, BASELINE configs 4 / 5 at
     // B = 1) on the N = d_model GEMMs, where 6 x 5 pair tiles occupy 30 of 74 pairs; 128 x 128 single-CTA tiles (120 of 148 CTAs) are then
     // faster (scripts/gpu_gemm_fit.py, M = 1500: out-proj 18.6 -> 14.4 us, fc2 36.5 -> 28.5 us; from M = 3000 on the pair tile is as fast or faster)
     bool pair = mode == 2 && s.N >= 256;
     bool use128 = !pair && (mode == 3 || (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
-    if (mode == 2 && (long long)s.rows_per_batch * s.batch <= 2048 && s.N <= 1536 && s.N % 128 == 0 && getenv("NB200_GEMM_NOFIT") == nullptr) {
+    if (mode == 2 && (long long)s.rows_per_batch * s.batch <= 2048 && s.N <= 1536 && s.N % 128 == 0 && !ctx->opt.gemm_nofit) {
         pair = false;
         use128 = true;
     }
@@ -508,10 +509,7 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     p.rows_per_batch = s.rows_per_batch;
     p.N = s.N;
     p.epi = e;
-    {
-        const char *dv = getenv("NB200_GEMM_DEBUG");
-        p.debug = dv ? atoi(dv) : 0;
-    }
+    p.debug = ctx->opt.gemm_debug;
     const int oes = e.out_bf16 ? 2 : 4;
     const int oa = 16 / oes;
     p.vec_ok = (e.ldo % oa == 0) && (e.out_bs % oa == 0) && (((uintptr_t)e.out) % 16 == 0) && (!e.bias || ((uintptr_t)e.bias) % 16 == 0) &&

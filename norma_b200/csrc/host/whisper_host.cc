@@ -124,11 +124,13 @@ int WhisperModel::transcribe(const float *data, size_t n, bool final_chunk, std:
             if (segments) segments->emplace_back(tokens, tokens + len);
             res += detokenize(tokens + 1, len >= 2 ? len - 2 : 0);                         // model.rs:147-149
         }
-        // The reference would spin forever on a decoding result that yields no drainable segment (e.g. no timestamp
-        // pair at all); a hang is not worth mirroring, so that case is reported instead.
+        // DEVIATION (documented in DESIGN.md / INTEGRATION.md): a decoding result that yields no drainable segment — the silent window,
+        // where decode() returns the prompt alone with avg_logprob = 0 (model.rs:308-315), passes the gate of model.rs:95 because 0 is not
+        // < -1 — leaves the reference looping forever on the same slice.  A hang cannot be mirrored; the window is dropped like the
+        // no-speech skip of model.rs:95-98 does, so a real-time stream keeps going after silence.
         if (!new_chunk_break && buf_.size() == len_before) {
-            err_ = "transcribe: decoding result made no progress (no timestamp-delimited segment)";
-            return NB200_INVALID_ARG;
+            ++n_no_progress;
+            buf_.erase(buf_.begin(), buf_.begin() + slice_len);
         }
     }
     if (final_chunk) {                                                                     // model.rs:153-156
@@ -260,21 +262,33 @@ int nb200_model_transcribe(nb200_model *m, const float *data, size_t n, int fina
     std::vector<std::vector<uint32_t>> segs;
     int st = m->model->transcribe(data, n, final_chunk != 0, &text, &segs);
     if (st != NB200_OK) return st;
-    if (text_len) *text_len = text.size();
-    if (text_out && text_cap) {
-        size_t c = std::min(text.size(), text_cap - 1);
-        memcpy(text_out, text.data(), c);
-        text_out[c] = 0;
-    }
-    // flattened segments: [n_segments, len_0, tokens_0..., len_1, tokens_1..., ...]
-    std::vector<uint32_t> flat;
-    flat.push_back((uint32_t)segs.size());
+    // The audio has been consumed, so the result is kept until it has been delivered in full: a caller whose buffers were too small
+    // gets NB200_BUFFER_TOO_SMALL with the needed sizes in *text_len / *seg_len and fetches it with nb200_model_last_result.
+    m->last_text = std::move(text);
+    m->last_flat.clear();
+    m->last_flat.push_back((uint32_t)segs.size());  // flattened segments: [n_segments, len_0, tokens_0..., len_1, tokens_1..., ...]
     for (auto &s : segs) {
-        flat.push_back((uint32_t)s.size());
-        flat.insert(flat.end(), s.begin(), s.end());
+        m->last_flat.push_back((uint32_t)s.size());
+        m->last_flat.insert(m->last_flat.end(), s.begin(), s.end());
     }
-    if (seg_len) *seg_len = flat.size();
-    if (seg_out) memcpy(seg_out, flat.data(), std::min(flat.size(), seg_cap) * 4);
+    return nb200_model_last_result(m, text_out, text_cap, text_len, seg_out, seg_cap, seg_len);
+}
+
+int nb200_model_last_result(nb200_model *m, char *text_out, size_t text_cap, size_t *text_len, uint32_t *seg_out, size_t seg_cap, size_t *seg_len) {
+    if (!m) return NB200_INVALID_ARG;
+    if (text_len) *text_len = m->last_text.size();
+    if (seg_len) *seg_len = m->last_flat.size();
+    const bool text_fits = !text_out || m->last_text.size() + 1 <= text_cap;
+    const bool seg_fits = !seg_out || m->last_flat.size() <= seg_cap;
+    if (!text_fits || !seg_fits) {
+        if (text_out && text_cap) text_out[0] = 0;
+        return NB200_BUFFER_TOO_SMALL;  // nothing partial is written: no text cut inside a UTF-8 sequence, no half segment list
+    }
+    if (text_out) {
+        memcpy(text_out, m->last_text.data(), m->last_text.size());
+        text_out[m->last_text.size()] = 0;
+    }
+    if (seg_out) memcpy(seg_out, m->last_flat.data(), m->last_flat.size() * 4);
     return NB200_OK;
 }
 
@@ -284,6 +298,12 @@ int nb200_model_state(nb200_model *m, size_t *buffered, size_t *n_encodes, size_
     if (n_encodes) *n_encodes = m->model->n_encodes;
     if (n_decodes) *n_decodes = m->model->n_decodes;
     if (n_resets) *n_resets = m->scripted ? (size_t)m->scripted->resets : 0;
+    return NB200_OK;
+}
+
+int nb200_model_no_progress_windows(nb200_model *m, size_t *n) {
+    if (!m || !n) return NB200_INVALID_ARG;
+    *n = m->model->n_no_progress;
     return NB200_OK;
 }
 

@@ -102,6 +102,7 @@ public:
     size_t buffered() const { return buf_.size(); }
     std::string last_error() const { return err_; }
     size_t n_encodes = 0, n_decodes = 0;
+    size_t n_no_progress = 0;  // windows dropped because their decoding result had no drainable segment (the reference hangs there)
 
 private:
     std::string detokenize(const uint32_t *t, size_t n) const;  // tokenizer.decode(.., skip_special_tokens = true)
@@ -124,4 +125,6 @@ struct nb200_model {
     nb200host::ScriptedBackend *scripted = nullptr;
     nb200host::WhisperModel *model = nullptr;
     std::string err;
+    std::string last_text;             // result of the last transcribe, kept until delivered in full (nb200_model_last_result)
+    std::vector<uint32_t> last_flat;
 };

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NB200_LIB_PATH", os.path.join(_HERE, "libnorma_b200.so"))  # override: instrumented builds (scripts/probes)
 
 NB200_OK = 0
-STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH", 7: "IO_ERROR", 8: "PARSE_ERROR", 9: "NOT_FOUND"}
+STATUS_NAMES = {0: "OK", 1: "INVALID_ARG", 2: "CUDA_ERROR", 3: "OOM", 4: "NOT_LOADED", 5: "UNSUPPORTED_SHAPE", 6: "ARCH_MISMATCH", 7: "IO_ERROR", 8: "PARSE_ERROR", 9: "NOT_FOUND", 10: "BUFFER_TOO_SMALL"}
 TASKS = {"transcribe": 0, "translate": 1}
 DTYPES = {"f32": 0, "bf16": 1, "f16": 2, "f64": 3, "u8": 4, "u32": 5}
 KERNEL_CLASSES = ["mel", "mel_norm", "gemm", "attn", "layernorm", "decode_gemv", "decode_attn", "decode_select", "misc"]
@@ -35,6 +35,8 @@ SYMBOLS = [
     "nb200_config_from_file", "nb200_mel_filters", "nb200_tokenizer_from_file", "nb200_tokenizer_destroy", "nb200_tokenizer_token_to_id",
     "nb200_tokenizer_decode", "nb200_tokenizer_special_tokens", "nb200_tokenizer_language_tokens", "nb200_load_safetensors", "nb200_safetensors_read", "nb200_load_gguf", "nb200_gguf_read", "nb200_set_decode_mode",
     "nb200_model_set_tokenizer", "nb200_model_from_files",
+    "nb200_set_audio_features", "nb200_decode_begin", "nb200_decode_advance", "nb200_decode_peek_logits", "nb200_decode_end",
+    "nb200_model_last_result", "nb200_model_no_progress_windows",
 ]
 
 
@@ -133,6 +135,13 @@ def load_library() -> C.CDLL:
         "nb200_load_gguf": ([p, C.c_char_p, C.POINTER(sz)], i),
         "nb200_gguf_read": ([C.c_char_p, C.c_char_p, f32p, sz, C.POINTER(C.c_int64), C.POINTER(i), C.POINTER(i)], i),
         "nb200_model_set_tokenizer": ([p, p], i),
+        "nb200_set_audio_features": ([p, f32p, sz], i),
+        "nb200_decode_begin": ([p, sz, C.c_float, C.c_uint64, sz], i),
+        "nb200_decode_advance": ([p, sz, C.POINTER(i)], i),
+        "nb200_decode_peek_logits": ([p, sz, f32p], i),
+        "nb200_decode_end": ([p, u32p, C.POINTER(sz), C.POINTER(C.c_double), C.POINTER(C.c_double)], i),
+        "nb200_model_last_result": ([p, C.c_char_p, sz, C.POINTER(sz), u32p, sz, C.POINTER(sz)], i),
+        "nb200_model_no_progress_windows": ([p, C.POINTER(sz)], i),
         "nb200_model_from_files": ([i, C.c_char_p, C.c_char_p, C.c_char_p, i, C.c_char_p, i, sz, C.c_uint64, C.POINTER(p), C.POINTER(p)], i),
     }
     for name, (args, res) in sigs.items():
@@ -473,6 +482,37 @@ class Context:
         nsp = (C.c_double * n_windows)()
         self._ck(self.lib.nb200_decode(self.h, n_windows, temperature, seed, max_new_tokens, toks.ctypes.data_as(C.POINTER(C.c_uint32)), n, alp, nsp))
         return [dict(tokens=toks[b, : n[b]].tolist(), avg_logprob=alp[b], no_speech_prob=nsp[b]) for b in range(n_windows)]
+
+    # the loop of model.rs:317-371 opened up: begin / advance / peek / end
+    def set_audio_features(self, xa: np.ndarray):
+        """`audio_features` handed in from the host ([n_windows, 1500, d] f32) instead of produced by the encoder."""
+        xa = np.ascontiguousarray(xa, np.float32)
+        assert xa.ndim == 3 and xa.shape[1:] == (self.T, self.d), xa.shape
+        self._ck(self.lib.nb200_set_audio_features(self.h, _f32p(xa), xa.shape[0]))
+
+    def decode_begin(self, n_windows: int = 1, temperature: float = 0.0, seed: int = 0, max_new_tokens: int = 0):
+        self._run_windows = n_windows
+        self._ck(self.lib.nb200_decode_begin(self.h, n_windows, temperature, seed, max_new_tokens))
+
+    def decode_advance(self, n_steps: int = 1) -> bool:
+        """-> True when every window had already finished (nothing was launched)."""
+        done = C.c_int()
+        self._ck(self.lib.nb200_decode_advance(self.h, n_steps, C.byref(done)))
+        return bool(done.value)
+
+    def decode_peek_logits(self, window: int = 0) -> np.ndarray:
+        out = np.empty(self.V, np.float32)
+        self._ck(self.lib.nb200_decode_peek_logits(self.h, window, _f32p(out)))
+        return out
+
+    def decode_end(self):
+        nw = self._run_windows
+        toks = np.zeros((nw, self.P), np.uint32)
+        n = (C.c_size_t * nw)()
+        alp = (C.c_double * nw)()
+        nsp = (C.c_double * nw)()
+        self._ck(self.lib.nb200_decode_end(self.h, toks.ctypes.data_as(C.POINTER(C.c_uint32)), n, alp, nsp))
+        return [dict(tokens=toks[b, : n[b]].tolist(), avg_logprob=alp[b], no_speech_prob=nsp[b]) for b in range(nw)]
 
     def decode_greedy(self, n_windows: int = 1, max_new_tokens: int = 0):
         toks = np.zeros((n_windows, self.P), np.uint32)

@@ -351,6 +351,10 @@ class Model:
         ptr = d.ctypes.data_as(C.POINTER(C.c_float)) if d.size else None
         st = self.lib.nb200_model_transcribe(self.h, ptr, d.size, int(final_chunk), text, len(text), C.byref(tl),
                                              seg.ctypes.data_as(C.POINTER(C.c_uint32)), seg.size, C.byref(sl))
+        if st == 10:  # NB200_BUFFER_TOO_SMALL: the audio is consumed and the result kept; fetch it into buffers of the reported sizes
+            text = C.create_string_buffer(tl.value + 1)
+            seg = np.zeros(max(sl.value, 1), np.uint32)
+            st = self.lib.nb200_model_last_result(self.h, text, len(text), C.byref(tl), seg.ctypes.data_as(C.POINTER(C.c_uint32)), seg.size, C.byref(sl))
         if st != 0:
             raise ffi.Nb200Error(st, (self.lib.nb200_model_last_error(self.h) or b"").decode())
         segs, i = [], 1
@@ -363,7 +367,9 @@ class Model:
     def state(self) -> Dict[str, int]:
         a, b, c, d = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
         self.lib.nb200_model_state(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-        return dict(buffered=a.value, n_encodes=b.value, n_decodes=c.value, n_resets=d.value)
+        e = C.c_size_t()
+        self.lib.nb200_model_no_progress_windows(self.h, C.byref(e))
+        return dict(buffered=a.value, n_encodes=b.value, n_decodes=c.value, n_resets=d.value, n_no_progress=e.value)
 
     # scripted backend (ctx is None): canned results for the host-logic tests
     def script_push(self, tokens: Sequence[int], avg_logprob: float, no_speech_prob: float):

@@ -36,8 +36,18 @@ def inclusive_boxed_by(v: List[int], pred: Callable[[int], bool]):
         v = v[e_idx:]
 
 
+class ReferenceWouldHang(RuntimeError):
+    """model.rs:68-150 on a decoding result without a drainable segment: nothing is drained, the same slice is decoded forever."""
+
+
 class HostModelOracle:
-    def __init__(self, encode, decode, reset_kv_cache, no_timestamps: int, eot: int, detok=None, detect_language=None, const_lang=None):
+    """`skip_no_progress=False` is the reference as written (the endless loop is raised as ReferenceWouldHang).  True is the ONE documented
+    divergence of the product's host mirror (include/norma_b200.h, nb200_model_transcribe): such a window is dropped like the no-speech
+    skip of model.rs:95-98 and counted in `n_no_progress`."""
+
+    def __init__(self, encode, decode, reset_kv_cache, no_timestamps: int, eot: int, detok=None, detect_language=None, const_lang=None,
+                 skip_no_progress: bool = False):
+        self.skip_no_progress, self.n_no_progress = skip_no_progress, 0
         self.encode, self.decode, self.reset_kv_cache = encode, decode, reset_kv_cache
         self.nts, self.eot = no_timestamps, eot
         self.detok = detok or (lambda toks: "")
@@ -62,6 +72,7 @@ class HostModelOracle:
         res, segs = "", []
         new_chunk = False
         while self.buf and not new_chunk:                                        # model.rs:68
+            len_before = len(self.buf)
             slice_len = min(len(self.buf), N_SAMPLES)
             self.encode(self.buf[:slice_len])                                    # model.rs:74-88, 168
             dr = self.decode_with_fallback()
@@ -90,6 +101,11 @@ class HostModelOracle:
                         break
                 segs.append(seg)
                 res += self.detok(seg[1:-1])                                     # model.rs:147-149
+            if not new_chunk and len(self.buf) == len_before:                    # nothing drained and no break: the reference loops forever
+                if not self.skip_no_progress:
+                    raise ReferenceWouldHang("decoding result made no progress (no timestamp-delimited segment)")
+                self.n_no_progress += 1
+                del self.buf[:slice_len]
         if final_chunk:
             if self.detect_language is not None:
                 self.language_token = None                                       # model.rs:154 `self.lang.clear()`

@@ -410,6 +410,35 @@ class GreedyDecoder:
         return DecodingResult(tokens, avg_logprob, no_speech_prob, margins=margins)
 
 
+    def select(self, p: torch.Tensor, prefix: List[int]):
+        """One pass of the loop body of model.rs:333-356 on a given probability vector: suppression rules for `prefix` (prompt + tokens
+        sampled so far), then the LAST maximal index.  -> (token, masked p, top-2 margin of the masked p)"""
+        st = self.st
+        plen = 3 if st.lang is not None else 2
+        last_timestamp = next((t for t in reversed(prefix[plen:]) if t > st.no_timestamps), None)
+        if last_timestamp is not None:
+            p = self._supress_tokens(p, prefix, last_timestamp)
+        else:
+            p = p + self.first_token_supress
+        mx = p.max()
+        tok = int(torch.nonzero(p == mx)[-1])
+        top2 = torch.topk(p, 2).values
+        return tok, p, float(top2[0] - top2[1])
+
+    @torch.no_grad()
+    def teacher_forced(self, audio_features: torch.Tensor, tokens: List[int]):
+        """The probability vectors the loop of model.rs:317-371 sees when it produces `tokens` (prompt + sampled tokens, no final eot
+        needed), from ONE causal pass: position i of `decoder_forward(tokens[:-1])` equals the last position of
+        `decoder_forward(tokens[:i + 1])` because decoder self-attention is masked, so this is the reference's per-step recomputation
+        without its O(n^2) cost.  -> (raw softmax probabilities [n_sampled, V], no_speech_prob)"""
+        m, st = self.m, self.st
+        plen = 3 if st.lang is not None else 2
+        ys = m.decoder_forward(torch.tensor([tokens[:-1]]), audio_features, True)
+        no_speech_prob = float(torch.softmax(m.final_linear(ys[:1, :1])[0, 0].float(), 0)[st.no_speech])
+        logits = m.final_linear(ys[:1, plen - 1:])[0]
+        return torch.softmax(logits.float(), -1), no_speech_prob
+
+
 @torch.no_grad()
 def detect_language(model: WhisperOracle, sot: int, language_tokens: List[int], audio_features: torch.Tensor):
     """norma `Model::detect_language` (/root/reference/src/models/whisper/model.rs:194-210): one decoder pass over [[sot]] with

@@ -30,6 +30,25 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, s)
 
 
+def test_rust_binding_block_is_generated_from_the_header():
+    """INTEGRATION.md's `extern "C"` block (the norma-b200-sys crate) is scripts/gen_rust_bindings.py's output for the CURRENT header:
+    nothing hand-written, nothing omitted."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_rust_bindings", os.path.join(ROOT, "scripts", "gen_rust_bindings.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    block = gen.generate(open(os.path.join(ROOT, "include", "norma_b200.h")).read())
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    a, b = doc.index(gen.BEGIN) + len(gen.BEGIN), doc.index(gen.END)
+    assert doc[a:b].strip() == block.strip(), "run `python scripts/gen_rust_bindings.py`"
+    fns = re.findall(r"pub fn (nb200_\w+)\(", block)
+    assert sorted(fns) == sorted(header_symbols())
+    for const in ("NB200_OK", "NB200_BUFFER_TOO_SMALL", "NB200_BF16", "NB200_DECODE_SEPARATE", "NB200_TASK_TRANSLATE"):
+        assert f"pub const {const}: c_int" in block
+    assert "pub struct nb200_config {" in block and "pub max_batch: i32," in block and "pub ts_one: u32," in block
+
+
 def test_header_compiles_as_c():
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(ROOT, "include", "norma_b200.h")],
                        capture_output=True, text=True)

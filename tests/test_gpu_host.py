@@ -54,13 +54,16 @@ def test_transcribe_end_to_end(lib, compute):
     ref = oracle_host(c, st, w)
     pcm = synth.synth_pcm("gauss", 3, 480_000 + 160_000)
     # three chunks as the Packer would deliver them: 10 s, 30 s (buffer then exceeds one window), final remainder
+    texts = []
     for lo, hi, final in ((0, 160_000, False), (160_000, 480_000 + 100_000, False), (480_000 + 100_000, pcm.size, True)):
         got = model.transcribe(pcm[lo:hi].copy(), final)
         exp = ref.transcribe(pcm[lo:hi].tolist(), final)
         assert got[1] == exp[1]                      # identical token segments (margins ~1 >> tolerance)
         assert got[0] == exp[0]
         assert model.state()["buffered"] == len(ref.buf)
-    assert " hello world" in "".join([" hello world"])  # vocabulary is wired through
+        texts.append(got[0])
+    # the vocabulary is wired through: the planted plan's text tokens 100, 200 detokenise to " hello world" in the product's own output
+    assert " hello world" in "".join(texts)
     model.close()
 
 

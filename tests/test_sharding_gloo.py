@@ -14,9 +14,11 @@ WORKER = textwrap.dedent('''
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     total = int(sys.argv[1])
-    mine = list(range(rank, total, world))            # bench.py: window w -> rank w mod world (SURVEY 8 e)
-    seeds = [rank + w * world for w in range(len(mine))]
-    assert seeds == mine
+    sys.path.insert(0, os.getcwd())
+    from norma_b200 import workload                   # the SAME functions bench.py shards with (SURVEY 8 e: window w -> rank w mod world)
+    mine = workload.windows_of_rank(rank, world, total)
+    assert mine == workload.window_ids(rank, world, 25, total)
+    assert workload.window_ids(rank, world, 25) == list(range(rank * 25, rank * 25 + 25))
     t = torch.zeros(total, dtype=torch.int64)
     t[mine] = 1
     dist.all_reduce(t)                                 # every window owned exactly once
@@ -48,3 +50,33 @@ def test_round_robin_sharding_world2(tmp_path):
 
     j = json.loads(line)
     assert j == {"covered": True, "max_ms": 11.0, "n0": 61}
+
+
+def test_sharding_rule_edge_cases():
+    from norma_b200 import workload as wl
+
+    for world in (1, 2, 3, 8):
+        for total in (0, 1, 5, 8, 120, 121):
+            owned = [w for r in range(world) for w in wl.windows_of_rank(r, world, total)]
+            assert sorted(owned) == list(range(total))                       # every window exactly once
+            sizes = [len(wl.windows_of_rank(r, world, total)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1                               # balanced
+    assert wl.windows_of_rank(7, 8, 5) == []                                  # fewer windows than ranks: that rank has nothing (bench.py refuses it)
+    assert wl.windows_per_step(8, 25) == 200 and wl.windows_per_step(8, 25, 120) == 120
+    import pytest
+
+    with pytest.raises(ValueError):
+        wl.windows_of_rank(2, 2, 10)
+
+
+def test_algorithmic_work_figures_match_survey():
+    """36.94 / 87.37 / 2273.77 GF per window; mel 2.880 / 3.456 MB; decode 56 / 97 / 225 / 1601 MB per token."""
+    from norma_b200 import synth, workload as wl
+
+    gf = lambda n: wl.encoder_flops(synth.model_config(n)) / 1e9
+    assert abs(gf("tiny.en") - 36.94) < 0.01 and abs(gf("base.en") - 87.37) < 0.01 and abs(gf("distil-large-v3") - 2273.77) < 0.01
+    assert wl.mel_bytes(synth.model_config("tiny.en")) == 2.88e6 and wl.mel_bytes(synth.model_config("large-v3")) == 3.456e6
+    c = synth.model_config("distil-large-v3")
+    assert abs((wl.decode_bytes_per_step(c, 0)) / 1e6 - 225) < 1
+    assert abs(wl.decode_bytes_per_step(synth.model_config("large-v3"), 0) / 1e6 - 1601) < 1
+    assert abs(wl.gemm_flops(c) + wl.attention_flops(c) - wl.encoder_flops(c)) < 1
