@@ -8,7 +8,14 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
            "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-           "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "lts__t_sector_hit_rate.pct"]
+           "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "lts__t_sector_hit_rate.pct",
+           "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.per_cycle_active",
+           "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+           "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+           "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum",
+           "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "memory_l2_theoretical_sectors_local", "launch__stack_size",
+           "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__pcsamp_sample_count"]
 SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
 
@@ -64,12 +71,21 @@ def full(tag, name):
             if m in hdr:
                 i = hdr.index(m)
                 f.write(f"| {m} | {units[i]} | " + " | ".join(r[i] for r in rows[2:]) + " |\n")
+        # warp-stall sampling: the five largest reasons of each launch, as a share of its samples
+        pref = "smsp__pcsamp_warps_issue_stalled_"
+        st = [(h[len(pref):], i) for i, h in enumerate(hdr) if h.startswith(pref) and not h.endswith("_not_issued")]
+        cells = []
+        for r in rows[2:]:
+            v = sorted(((float(r[i] or 0), n) for n, i in st), reverse=True)
+            tot = sum(x for x, _ in v) or 1.0
+            cells.append(", ".join(f"{n} {100 * x / tot:.0f}%" for x, n in v[:5]))
+        f.write("| top warp-stall reasons (pc sampling) | share of samples | " + " | ".join(cells) + " |\n")
 
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     os.makedirs(PROF, exist_ok=True)
-    launch_list(tag, "python bench.py --windows 8 --steps 2 --warmup 3 --no-cpu-baseline")
+    launch_list(tag, os.environ.get("NCU_CMD", "python bench.py --quick --windows 8 --steps 2 --warmup 3 --no-cpu-baseline"))
     for n in sys.argv[2:] or ["gemm", "attn", "melln"]:
         full(tag, n)
     print(sorted(os.listdir(PROF)))
