@@ -127,8 +127,31 @@ int up_mat(nb200_ctx *ctx, const std::string &name, size_t n, void **out) {
     return upload_compute(ctx, t->data, out);
 }
 
-// concatenated [q | k | v] weight and bias ([3d][d], [3d] with zeros for the bias-less k_proj)
-int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b) {
+// Fold the LayerNorm in front of a linear layer into it (ctx->ln_fold).  LN(x) = (x - mean(x)) . rstd . gamma + beta and the centring is
+// itself linear (x - mean(x) = x . (I - 11^T / K)), so with W' = W . diag(gamma) . (I - 11^T / K) — every row of W . diag(gamma) minus its own
+// mean — and b' = b + W . beta:   LN(x) . W^T + b = rstd . (x . W'^T) + b'.
+// The consuming GEMM multiplies the bf16 copy of x with W' and applies the row's rstd in its epilogue (gemm_tcgen05.cu).
+int fold_layernorm(nb200_ctx *ctx, const std::string &ln, int N, int K, std::vector<float> &W, std::vector<float> &B) {
+    const HostTensor *g = nullptr, *bt = nullptr;
+    NB_TRY(need(ctx, ln + ".weight", K, &g));
+    NB_TRY(need(ctx, ln + ".bias", K, &bt));
+    for (int n = 0; n < N; ++n) {
+        float *w = W.data() + (size_t)n * K;
+        double acc_b = 0.0, acc_s = 0.0;
+        for (int k = 0; k < K; ++k) {
+            acc_b += (double)w[k] * bt->data[k];
+            w[k] *= g->data[k];
+            acc_s += (double)w[k];
+        }
+        const float m = (float)(acc_s / K);
+        for (int k = 0; k < K; ++k) w[k] -= m;
+        B[n] += (float)acc_b;
+    }
+    return NB200_OK;
+}
+
+// concatenated [q | k | v] weight and bias ([3d][d], [3d] with zeros for the bias-less k_proj); `fold_ln`: the LayerNorm to fold in
+int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b, const std::string &fold_ln = "") {
     const HostTensor *q = nullptr, *k = nullptr, *v = nullptr, *bq = nullptr, *bv = nullptr;
     NB_TRY(need(ctx, p + "q_proj.weight", (size_t)d * d, &q));
     NB_TRY(need(ctx, p + "k_proj.weight", (size_t)d * d, &k));
@@ -141,6 +164,7 @@ int up_qkv(nb200_ctx *ctx, const std::string &p, int d, void **w, float **b) {
     memcpy(W.data() + (size_t)2 * d * d, v->data.data(), (size_t)d * d * 4);
     memcpy(B.data(), bq->data.data(), d * 4);
     memcpy(B.data() + 2 * d, bv->data.data(), d * 4);
+    if (!fold_ln.empty()) NB_TRY(fold_layernorm(ctx, fold_ln, 3 * d, d, W, B));
     NB_TRY(upload_compute(ctx, W, w));
     return upload_f32(ctx, B, b);
 }
@@ -268,22 +292,42 @@ int encoder_run(nb200_ctx *ctx, int B) {
         NB_TRY(gemm(ctx->melT, ctx->conv1_w, s, e));
     }
     // conv2 (k3, s2, p1) + GELU + sinusoidal positions -> residual stream x [B*1500][d] f32
+    // With ctx->ln_fold the LayerNorms before QKV and fc1 do not exist as kernels: every GEMM that writes the residual stream (conv2, out-proj,
+    // fc2) also writes its bf16 copy into `h` and per-row partial (mean, M2); the consuming GEMM multiplies the copy with W . diag(gamma) and
+    // finishes the normalisation in its epilogue (gemm_tcgen05.cu).
+    const bool fold = ctx->ln_fold;
+    const long long Mmax = (long long)c.max_batch * T;
+    auto produce = [&](Epilogue &e) {
+        if (!fold) return;
+        e.xb_out = (bf16 *)ctx->h;
+        e.stats_out = ctx->ln_stats;
+        e.stats_ld = Mmax;
+    };
+    auto consume = [&](Epilogue &e) {
+        if (!fold) return;
+        e.stats_in = ctx->ln_stats;
+        e.stats_ld = Mmax;
+        e.stats_slots = ctx->ln_slots;
+        e.stats_cols = ctx->ln_slot_cols;
+    };
     {
         GemmShape s{T, B, d, 3 * d, 2 * d, (long long)(N_FRAMES + 1) * d};
         Epilogue e{};
         e.bias = ctx->conv2_b; e.act = 1;
         e.residual = ctx->pos; e.ldr = d; e.res_bs = 0;
         e.out = ctx->x; e.ldo = d; e.out_bs = (long long)T * d; e.out_bf16 = 0;
+        produce(e);
         NB_TRY(gemm(ctx->y1, ctx->conv2_w, s, e));
     }
     for (int l = 0; l < c.encoder_layers; ++l) {
         const EncLayer &w = ctx->enc[l];
-        NB_TRY(launch_layernorm(ctx, ctx->x, w.ln1g, w.ln1b, M, d, ctx->h, bf, nullptr));
+        if (!fold) NB_TRY(launch_layernorm(ctx, ctx->x, w.ln1g, w.ln1b, M, d, ctx->h, bf, nullptr));
         {
             GemmShape s{M, 1, 3 * d, d, d, (long long)M * d};
             Epilogue e{};
             e.bias = w.bqkv; e.scale = qk_scale; e.n_scale = 2 * d;  // q and k each scaled by hd^-0.25
             e.out = ctx->qkv; e.ldo = 3 * d; e.out_bf16 = bf;
+            consume(e);
             NB_TRY(gemm(ctx->h, w.wqkv, s, e));
         }
         if (bf && ctx->opt.attn_tc) NB_TRY(launch_attention_tc(ctx, (const bf16 *)ctx->qkv, (bf16 *)ctx->attn, B, T, H));
@@ -293,14 +337,16 @@ int encoder_run(nb200_ctx *ctx, int B) {
             Epilogue e{};
             e.bias = w.bo; e.residual = ctx->x; e.ldr = d;
             e.out = ctx->x; e.ldo = d; e.out_bf16 = 0;
+            produce(e);
             NB_TRY(gemm(ctx->attn, w.wo, s, e));
         }
-        NB_TRY(launch_layernorm(ctx, ctx->x, w.ln2g, w.ln2b, M, d, ctx->h, bf, nullptr));
+        if (!fold) NB_TRY(launch_layernorm(ctx, ctx->x, w.ln2g, w.ln2b, M, d, ctx->h, bf, nullptr));
         {
             GemmShape s{M, 1, 4 * d, d, d, (long long)M * d};
             Epilogue e{};
             e.bias = w.b1; e.act = 1;
             e.out = ctx->ff; e.ldo = 4 * d; e.out_bf16 = bf;
+            consume(e);
             NB_TRY(gemm(ctx->h, w.w1, s, e));
         }
         {
@@ -308,6 +354,7 @@ int encoder_run(nb200_ctx *ctx, int B) {
             Epilogue e{};
             e.bias = w.b2; e.residual = ctx->x; e.ldr = d;
             e.out = ctx->x; e.ldo = d; e.out_bf16 = 0;
+            if (l + 1 < c.encoder_layers) produce(e);  // ln_post stays a kernel: nothing consumes the last layer's copy
             NB_TRY(gemm(ctx->ff, w.w2, s, e));
         }
     }
@@ -434,6 +481,7 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
         o.gemm_epi_tma = is("NB200_EPI", "direct") ? 0 : 1;
         o.gemm_nofit = env("NB200_GEMM_NOFIT") != nullptr;
         o.gemm_debug = env("NB200_GEMM_DEBUG") ? atoi(env("NB200_GEMM_DEBUG")) : 0;
+        if (env("NB200_GEMM_NP")) o.gemm_np = std::min(4, std::max(2, atoi(env("NB200_GEMM_NP"))));
         o.attn_tc = is("NB200_ATTN", "simt") ? 0 : 1;
         o.decode_fused = (env("NB200_DECODE_FUSED") && env("NB200_DECODE_FUSED")[0] == '0') ? 0 : 1;
         o.decode_graph = env("NB200_DECODE_NOGRAPH") ? 0 : 1;
@@ -581,17 +629,35 @@ int nb200_finalize_weights(nb200_ctx *ctx) {
             }
         NB_TRY(upload_f32(ctx, pos, &ctx->pos));
     }
+    // LayerNorm folded into the encoder's QKV / fc1 GEMMs: the tcgen05 path only, on shapes whose N = d_model tiles are whole
+    ctx->ln_fold = ctx->compute == NB200_BF16 && ctx->opt.ln_fused && ctx->opt.gemm_epi_tma && (d % 256 == 0 || (d % 128 == 0 && d <= 1024)) &&
+                   2 * (d / 128) <= LN_MAX_SLOTS;
+    if (ctx->ln_fold) {
+        const size_t rows = (size_t)c.max_batch * c.max_source_positions;
+        NB_TRY(dev_alloc_t(ctx, (size_t)LN_MAX_SLOTS * rows, &ctx->ln_stats, true));
+    }
     ctx->enc.resize(c.encoder_layers);
     for (int l = 0; l < c.encoder_layers; ++l) {
         const std::string p = E + "layers." + std::to_string(l) + ".";
         EncLayer &w = ctx->enc[l];
-        NB_TRY(up_qkv(ctx, p + "self_attn.", d, &w.wqkv, &w.bqkv));
+        if (ctx->ln_fold) {
+            NB_TRY(up_qkv(ctx, p + "self_attn.", d, &w.wqkv, &w.bqkv, p + "self_attn_layer_norm"));
+            const HostTensor *w1 = nullptr, *b1 = nullptr;
+            NB_TRY(need(ctx, p + "fc1.weight", (size_t)4 * d * d, &w1));
+            NB_TRY(need(ctx, p + "fc1.bias", 4 * d, &b1));
+            std::vector<float> W = w1->data, Bv = b1->data;
+            NB_TRY(fold_layernorm(ctx, p + "final_layer_norm", 4 * d, d, W, Bv));
+            NB_TRY(upload_compute(ctx, W, &w.w1));
+            NB_TRY(upload_f32(ctx, Bv, &w.b1));
+        } else {
+            NB_TRY(up_qkv(ctx, p + "self_attn.", d, &w.wqkv, &w.bqkv));
+            NB_TRY(up_mat(ctx, p + "fc1.weight", (size_t)4 * d * d, &w.w1));
+            NB_TRY(up_vec(ctx, p + "fc1.bias", 4 * d, &w.b1));
+        }
         NB_TRY(up_mat(ctx, p + "self_attn.out_proj.weight", (size_t)d * d, &w.wo));
         NB_TRY(up_vec(ctx, p + "self_attn.out_proj.bias", d, &w.bo));
         NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.weight", d, &w.ln1g));
         NB_TRY(up_vec(ctx, p + "self_attn_layer_norm.bias", d, &w.ln1b));
-        NB_TRY(up_mat(ctx, p + "fc1.weight", (size_t)4 * d * d, &w.w1));
-        NB_TRY(up_vec(ctx, p + "fc1.bias", 4 * d, &w.b1));
         NB_TRY(up_mat(ctx, p + "fc2.weight", (size_t)4 * d * d, &w.w2));
         NB_TRY(up_vec(ctx, p + "fc2.bias", d, &w.b2));
         NB_TRY(up_vec(ctx, p + "final_layer_norm.weight", d, &w.ln2g));

@@ -22,6 +22,8 @@ constexpr int N_SAMPLES = 480000;
 constexpr int N_FRAMES = 3000;   // frames kept per window
 constexpr int HEAD_DIM = 64;
 constexpr int MEL_PAD_FRAMES = 1500;  // candle pads n_len by one 15 s chunk of zeros
+constexpr int LN_MAX_SLOTS = 20;      // fused LayerNorm: (d_model / 128 n-tiles) x 2 epilogue warp groups at most (d_model <= 1280)
+constexpr float LN_EPS = 1e-5f;       // candle_nn LayerNorm eps
 
 // ---------------------------------------------------------------------------------------------------------
 // GEMM epilogue description shared by the SIMT fp32 and the tcgen05 bf16 kernels.
@@ -40,6 +42,17 @@ struct Epilogue {
     int n_scale;
     int act;                // 0 none, 1 gelu(tanh)
     int out_bf16;           // 1: out is bf16, 0: f32
+    // ---- LayerNorm folded into the adjacent GEMMs (tcgen05 bf16 path only; DESIGN.md §4 "fused LayerNorm") ----
+    // producer (f32 out + residual = the new residual-stream rows): also writes a bf16 copy of the rows and per-row partial (mean, M2)
+    // slots, one per (n tile, epilogue warp group)
+    bf16 *xb_out;           // [rows][ldo] bf16 copy of out (same row addressing as out), or nullptr
+    float2 *stats_out;      // [slots][stats_ld] partial (mean, M2) per row, or nullptr
+    long long stats_ld;     // rows per slot plane
+    // consumer (A = the bf16 copy, W = W . diag(gamma) . (I - 11^T / K): gamma and the centring live in the weight):
+    // out = rstd . acc + bias[n], bias = b + W . beta, rstd from the row's slots
+    const float2 *stats_in; // the producer's slots for A's rows, or nullptr
+    int stats_slots;        // slots per row
+    int stats_cols;         // columns per slot
 };
 
 struct GemmShape {
@@ -50,8 +63,8 @@ struct GemmShape {
 };
 
 struct EncLayer {
-    void *wqkv, *wo, *w1, *w2;  // compute dtype
-    float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+    void *wqkv, *wo, *w1, *w2;  // compute dtype; with ctx->ln_fold: wqkv = Wqkv . diag(ln1 gamma) . (I - 11^T / d), w1 likewise with ln2
+    float *bqkv, *bo, *b1, *b2, *ln1g, *ln1b, *ln2g, *ln2b;  // with ctx->ln_fold: bqkv = b + Wqkv . beta1, b1 = b + W1 . beta2
 };
 struct DecLayer {
     void *wqkv, *wo, *cwq, *cwkv, *cwo, *w1, *w2;
@@ -71,6 +84,7 @@ struct CtxOptions {
     int gemm_epi_tma = 1;     // NB200_EPI=direct -> 0: thread-per-row stores
     int gemm_nofit = 0;       // NB200_GEMM_NOFIT: keep the pair tile for one window's worth of rows
     int gemm_debug = 0;       // NB200_GEMM_DEBUG: microbenchmark switches of gemm_tc_kernel
+    int gemm_np = 2;          // NB200_GEMM_NP: staging patches per epilogue warp of the f32-residual GEMMs (2, 3 or 4)
     int attn_tc = 1;          // NB200_ATTN=simt -> 0: CUDA-core attention
     int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels
     int decode_graph = 1;     // NB200_DECODE_NOGRAPH -> 0
@@ -142,7 +156,10 @@ struct nb200_ctx {
     // encoder activations
     void *y1 = nullptr;     // [max_batch][N_FRAMES+1][d] conv1 out, row 0 = zero pad (compute dtype)
     float *x = nullptr;     // [max_batch*1500][d] residual stream f32
-    void *h = nullptr;      // [M][d] LN out (compute dtype)
+    void *h = nullptr;      // [M][d] LN out (compute dtype); with ln_fold: the bf16 copy of the residual stream
+    bool ln_fold = false;   // LayerNorm folded into the encoder GEMMs (bf16 mode, d % 256 == 0, NB200_LN_FUSED != 0); decided at finalize
+    float2 *ln_stats = nullptr;  // [LN_MAX_SLOTS][max_batch*1500] per-row partial (mean, M2)
+    int ln_slots = 0, ln_slot_cols = 0;  // what the last producer launch wrote
     void *qkv = nullptr;    // [M][3d]
     void *attn = nullptr;   // [M][d]
     void *ff = nullptr;     // [M][4d]

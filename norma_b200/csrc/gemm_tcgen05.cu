@@ -43,18 +43,28 @@ struct GemmTcParams {
     Epilogue epi;
 };
 
-template <int BN, bool CTA2>
+// NP = staging patches per epilogue warp.  Two are enough without a residual (one being filled, one being stored).  With an f32
+// residual every chunk's residual is a TMA load the chunk has to wait for: NP patches keep NP loads in flight per warp, the first NP
+// issued while the mainloop of the tile still runs — with two, three of a 256-wide tile's four chunks each exposed most of an HBM round
+// trip (the out-proj GEMM ran at 3.3 TB/s of memory traffic, bound by neither pipe).  The third patch costs the pipeline one stage.
+template <int BN, bool CTA2, int NP>
 struct GemmCfg {
     static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;  // W rows this CTA loads per stage
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (STAGE_BYTES == 49152) ? 3 : 5;
+    static constexpr int STAGING = EPI_WARPS * NP * STG_BYTES;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr int LN_BYTES = 2 * BM * 4;  // 1 / std of the tile's rows, per accumulator stage (fused LayerNorm consumer)
+    static constexpr int SMEM_LIMIT = 232448;  // the 227 KB a CTA may opt in to
+    static constexpr int FIT = (SMEM_LIMIT - STAGING - 1024 - BAR_BYTES - LN_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > 5 ? 5 : FIT;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int TILE_M = CTA2 ? 256 : 128;
-    static constexpr int STAGING = EPI_WARPS * 2 * STG_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
-    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA may opt in to");
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + BAR_BYTES + LN_BYTES;
+    static_assert(STAGES >= 3, "pipeline too shallow");
+    static_assert((2 * STAGES + 9 + EPI_WARPS * NP) * 8 <= BAR_BYTES, "barrier block");
+    static_assert(SMEM_BYTES <= SMEM_LIMIT, "exceeds the 227 KB of shared memory a CTA may opt in to");
 };
 
 __device__ __forceinline__ float epi_math(float acc, float bias, float cs, int act) {
@@ -121,11 +131,81 @@ __device__ __forceinline__ float4 bias4(const Epilogue &e, int n, int N, bool fu
     return b;
 }
 
-template <int BN, bool CTA2>
+// ---- fused LayerNorm, producer side ---------------------------------------------------------------------------------
+// (mean, M2) of 32 values held in registers (two passes: exact to rounding whatever the mean), merged into the running partial
+// of this thread's row with Chan's update
+__device__ __forceinline__ void ln_stats_chunk(const uint32_t *v, float &cnt, float &mean, float &m2) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        s0 += __uint_as_float(v[i]); s1 += __uint_as_float(v[i + 1]); s2 += __uint_as_float(v[i + 2]); s3 += __uint_as_float(v[i + 3]);
+    }
+    const float cm = ((s0 + s1) + (s2 + s3)) * (1.0f / 32.0f);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float d0 = __uint_as_float(v[i]) - cm, d1 = __uint_as_float(v[i + 1]) - cm, d2 = __uint_as_float(v[i + 2]) - cm, d3 = __uint_as_float(v[i + 3]) - cm;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    const float cq = (q0 + q1) + (q2 + q3);
+    const float tot = cnt + 32.0f, delta = cm - mean, w = __fdividef(32.0f, tot);
+    mean = fmaf(delta, w, mean);
+    m2 += cq + delta * delta * cnt * w;
+    cnt = tot;
+}
+
+// bf16 copy of this thread's 32 values (one row of a 32-column chunk): 64 contiguous bytes as two 256-bit stores — whole 32-byte
+// sectors, no shuffles (16-byte thread-per-row stores leave every sector half-written per instruction and were measured to cap at
+// ~1.2 TB/s)
+__device__ __forceinline__ void ln_store_bf16_row(const uint32_t *v, bf16 *dst) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        pk[i] = *(uint32_t *)&t;
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]),
+                 "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                 : "memory");
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16), "r"(pk[8]), "r"(pk[9]), "r"(pk[10]), "r"(pk[11]),
+                 "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                 : "memory");
+}
+
+// the same copy for a 32-row x 32-column chunk with 16-byte stores: packed to 4 x 16 bytes per row, transposed inside each lane quad
+// with two butterfly stages so that in store k the four lanes of a quad write the 64 contiguous bytes of row (quad base + k)
+__device__ __forceinline__ void ln_store_bf16_chunk(const uint32_t *v, bf16 *dst_row0 /* row (quad base) of this chunk, column n0 */, long long ld, int lane,
+                                                    int rows_left /* valid rows from the quad base on */) {
+    uint4 a[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[8 * p + 0]), __uint_as_float(v[8 * p + 1]));
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[8 * p + 2]), __uint_as_float(v[8 * p + 3]));
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * p + 4]), __uint_as_float(v[8 * p + 5]));
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[8 * p + 6]), __uint_as_float(v[8 * p + 7]));
+        a[p].x = *(uint32_t *)&t0; a[p].y = *(uint32_t *)&t1; a[p].z = *(uint32_t *)&t2; a[p].w = *(uint32_t *)&t3;
+    }
+    const bool b0 = lane & 1, b1 = lane & 2;
+    auto xchg = [&](uint4 &lo, uint4 &hi, bool bit, int mask) {  // lanes with the bit clear keep lo and trade hi, the others the reverse
+        uint4 snd = bit ? lo : hi, rcv;
+        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, mask); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, mask);
+        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, mask); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, mask);
+        if (bit) lo = rcv; else hi = rcv;
+    };
+    xchg(a[0], a[1], b0, 1); xchg(a[2], a[3], b0, 1);
+    xchg(a[0], a[2], b1, 2); xchg(a[1], a[3], b1, 2);
+    // now a[k] = piece (lane & 3) of the row of quad lane k
+    bf16 *d = dst_row0 + 8 * (lane & 3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < rows_left) *(uint4 *)(d + (long long)k * ld) = a[k];
+}
+
+template <int BN, bool CTA2, int NP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const GemmTcParams p) {
-    using C = GemmCfg<BN, CTA2>;
+    using C = GemmCfg<BN, CTA2, NP>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_raw_u = ptx::smem_u32(smem_raw);
     const uint32_t smem_base = (smem_raw_u + 1023u) & ~1023u;
@@ -138,13 +218,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
     auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
     const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
-    auto res_bar = [&](int w, int buf) { return bars + 8u * (2 * C::STAGES + 5 + 2 * w + buf); };
+    auto res_bar = [&](int w, int buf) { return bars + 8u * (2 * C::STAGES + 5 + NP * w + buf); };
+    // fused LayerNorm (consumer): warp 3 merges the rows' partial statistics of every tile and publishes 1 / std per accumulator stage
+    auto lnfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 5 + NP * EPI_WARPS + s); };
+    auto lnempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 7 + NP * EPI_WARPS + s); };
+    float *ln_smem = (float *)(smem_raw + (bars + C::BAR_BYTES - smem_raw_u));  // [2][BM]
     volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_raw_u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTA2 ? ptx::cluster_ctarank() : 0u;
     const int first_tile = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // t-th tile of this CTA (pair) -> (row block mb, n tile); false when the CTA has run out of tiles.  All three roles walk the same sequence.
+    auto tile_at = [&](int t, int &mb, int &n_idx) -> bool {
+        const int tile = first_tile + t * tile_step;
+        n_idx = tile % p.n_tiles;
+        mb = tile / p.n_tiles;
+        return tile < p.total_tiles;
+    };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA);
@@ -164,8 +255,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(tempty_bar(s), CTA2 ? 2 * EPI_WARPS : EPI_WARPS);  // CTA2: both CTAs' warps arrive on the LEADER
         }
         for (int w = 0; w < EPI_WARPS; ++w) {
-            ptx::mbar_init(res_bar(w, 0), 1);
-            ptx::mbar_init(res_bar(w, 1), 1);
+            for (int k = 0; k < NP; ++k) ptx::mbar_init(res_bar(w, k), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(lnfull_bar(s), 1);
+            ptx::mbar_init(lnempty_bar(s), EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
@@ -190,8 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-                const int n_idx = tile % p.n_tiles, mb = tile / p.n_tiles;
+            int mb, n_idx;
+            for (int t = 0; tile_at(t, mb, n_idx); ++t) {
                 const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -217,7 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+            int mb_, n_idx_;
+            for (int t = 0; tile_at(t, mb_, n_idx_); ++t) {
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -240,6 +335,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
+    } else if (warp == 3) {
+        // ================= fused LayerNorm statistics (consumer side only) =================
+        // For every tile of this CTA, in order: merge the producer's partial (mean, M2) slots of the tile's 128 rows (Chan's update, equal
+        // column counts) and publish 1 / std in shared memory for the epilogue warps.  Lane l owns rows l, l + 32, l + 64, l + 96: every
+        // load is one coalesced 256-byte request and four rows' chains run side by side.  A whole mainloop is available per tile, so none of
+        // this is on the epilogue's critical path (merging the slots in the epilogue warps cost the QKV / fc1 GEMMs 15 %).
+        const Epilogue &e = p.epi;
+        if (e.stats_in != nullptr && p.use_tma && e.out_bf16) {
+            int as = 0;
+            uint32_t aphase = 0;
+            const float cols = (float)e.stats_cols;
+            int mb, n_idx;
+            for (int t = 0; tile_at(t, mb, n_idx); ++t) {
+                const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
+                const int r0 = mt * C::TILE_M + (int)rank * BM;
+                ptx::mbar_wait(lnempty_bar(as), aphase ^ 1u);
+                const float2 *sp = e.stats_in + (long long)b * p.rows_per_batch + r0 + lane;
+                float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+                bool ok[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ok[k] = r0 + lane + 32 * k < p.rows_per_batch;
+#pragma unroll 2
+                for (int i = 0; i < e.stats_slots; ++i) {
+                    float2 pm[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pm[k] = ok[k] ? __ldcg(sp + (long long)i * e.stats_ld + 32 * k) : make_float2(0.f, 1.f);
+                    const float tot = cnt + cols, w = __fdividef(cols, tot);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float delta = pm[k].x - mean[k];
+                        mean[k] = fmaf(delta, w, mean[k]);
+                        m2[k] += pm[k].y + delta * delta * cnt * w;
+                    }
+                    cnt = tot;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ln_smem[as * BM + lane + 32 * k] = rsqrtf(m2[k] / cnt + LN_EPS);
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(lnfull_bar(as));  // release: the stores above are ordered before the arrival
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
     } else if (warp >= 4) {
         // ================= epilogue: 8 warps = 2 per scheduler; warps (4+q) and (8+q) share TMEM lane quarter q and take
         // alternate column chunks =================
@@ -249,14 +386,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const Epilogue &e = p.epi;
         const bool has_res = e.residual != nullptr;
         const bool no_mem = (p.debug & 1) != 0;
-        const uint32_t stg = stg_base + (uint32_t)(ew * 2 * STG_BYTES);
+        const uint32_t stg = stg_base + (uint32_t)(ew * NP * STG_BYTES);
         uint8_t *stg_ptr = smem_raw + (stg - smem_raw_u);
         const int sw = lane & 7;
         uint32_t rphase = 0;  // bit b: parity of res_bar(ew, b)
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
-            const int n_idx = tile % p.n_tiles, mb = tile / p.n_tiles;
+        int mb, n_idx;
+        for (int t = 0; tile_at(t, mb, n_idx); ++t) {
             const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
             const int r0 = mt * C::TILE_M + (int)rank * BM + q * 32;  // this warp's first row
             const int nt0 = n_idx * BN;
@@ -265,6 +402,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.use_tma && !no_mem) {
                 if (e.out_bf16) {
                     // ---------- bf16 out: 64-column chunks (128 B rows), no residual ----------
+                    // fused LayerNorm (consumer): A is the bf16 copy of the residual stream and W carries gamma AND the centring
+                    // (W . diag(gamma) . (I - 11^T / K)), so all that is left of the LayerNorm is this row's 1 / std
+                    float ln_rstd = 1.0f;
+                    if (e.stats_in != nullptr) {  // published by the statistics warp (warp 3) for this accumulator stage
+                        ptx::mbar_wait(lnfull_bar(as), aphase);
+                        ln_rstd = ln_smem[as * BM + q * 32 + lane];
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(lnempty_bar(as));
+                    }
                     ptx::mbar_wait(tfull_bar(as), aphase);
                     ptx::tc_fence_after();
 #pragma unroll 1
@@ -287,10 +433,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [8j, 8j+8)
                             const float4 b0 = bias4(e, n0 + 8 * j, p.N, full), b1 = bias4(e, n0 + 8 * j + 4, p.N, full);
                             float v[8];
-                            v[0] = (__uint_as_float(acc[8 * j + 0]) + b0.x) * cs; v[1] = (__uint_as_float(acc[8 * j + 1]) + b0.y) * cs;
-                            v[2] = (__uint_as_float(acc[8 * j + 2]) + b0.z) * cs; v[3] = (__uint_as_float(acc[8 * j + 3]) + b0.w) * cs;
-                            v[4] = (__uint_as_float(acc[8 * j + 4]) + b1.x) * cs; v[5] = (__uint_as_float(acc[8 * j + 5]) + b1.y) * cs;
-                            v[6] = (__uint_as_float(acc[8 * j + 6]) + b1.z) * cs; v[7] = (__uint_as_float(acc[8 * j + 7]) + b1.w) * cs;
+                            v[0] = fmaf(__uint_as_float(acc[8 * j + 0]), ln_rstd, b0.x) * cs; v[1] = fmaf(__uint_as_float(acc[8 * j + 1]), ln_rstd, b0.y) * cs;
+                            v[2] = fmaf(__uint_as_float(acc[8 * j + 2]), ln_rstd, b0.z) * cs; v[3] = fmaf(__uint_as_float(acc[8 * j + 3]), ln_rstd, b0.w) * cs;
+                            v[4] = fmaf(__uint_as_float(acc[8 * j + 4]), ln_rstd, b1.x) * cs; v[5] = fmaf(__uint_as_float(acc[8 * j + 5]), ln_rstd, b1.y) * cs;
+                            v[6] = fmaf(__uint_as_float(acc[8 * j + 6]), ln_rstd, b1.z) * cs; v[7] = fmaf(__uint_as_float(acc[8 * j + 7]), ln_rstd, b1.w) * cs;
                             if (mixed) {  // a chunk straddling the scaled-column boundary (not hit by the Whisper shapes)
 #pragma unroll
                                 for (int t = 0; t < 8; ++t)
@@ -316,10 +462,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     // ---------- f32 out: 32-column chunks (128 B rows), optional f32 residual via TMA ----------
                     constexpr int NCI = BN / 64;  // chunks per warp
-                    if (has_res && lane == 0 && nt0 + grp * 32 < p.N) {  // first chunk's residual is fetched while the mainloop still runs
-                        ptx::bulk_wait_read<0>();
-                        ptx::mbar_expect_tx(res_bar(ew, 0), STG_BYTES);
-                        ptx::tma_load_3d(stg, &tmRes, res_bar(ew, 0), nt0 + grp * 32, r0, rb);
+                    const bool ln_out = e.stats_out != nullptr;  // fused LayerNorm (producer): bf16 copy + per-row partial statistics
+                    float ln_cnt = 0.f, ln_mean = 0.f, ln_m2 = 0.f;  // (count, mean, M2) of this thread's row over this warp's columns of the tile
+                    if (has_res && lane == 0) {  // the residual of the first NP chunks is fetched while the mainloop of this tile still runs
+                        ptx::bulk_wait_read<0>();  // the previous tile's stores no longer read the patches
+#pragma unroll
+                        for (int k = 0; k < (NP < NCI ? NP : NCI); ++k) {
+                            const int nk = nt0 + (2 * k + grp) * 32;
+                            if (nk < p.N) {
+                                ptx::mbar_expect_tx(res_bar(ew, k), STG_BYTES);
+                                ptx::tma_load_3d(stg + (uint32_t)(k * STG_BYTES), &tmRes, res_bar(ew, k), nk, r0, rb);
+                            }
+                        }
                     }
                     ptx::mbar_wait(tfull_bar(as), aphase);
                     ptx::tc_fence_after();
@@ -328,16 +482,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int c = 2 * ci + grp;
                         const int n0 = nt0 + c * 32;
                         if (n0 >= p.N) continue;  // warp-uniform
-                        const int buf = ci & 1;
+                        const int buf = has_res ? ci % NP : (ci & 1);
                         const uint32_t sb = stg + (uint32_t)(buf * STG_BYTES);
                         uint8_t *sbp = stg_ptr + buf * STG_BYTES + lane * 128;
                         uint32_t acc[32];
                         ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 32), acc);
                         if (has_res) {
-                            if (lane == 0 && ci + 1 < NCI && n0 + 64 < p.N) {  // this warp's next chunk, one ahead
-                                ptx::bulk_wait_read<0>();  // its previous store no longer reads the other patch
-                                ptx::mbar_expect_tx(res_bar(ew, buf ^ 1), STG_BYTES);
-                                ptx::tma_load_3d(stg + (uint32_t)((buf ^ 1) * STG_BYTES), &tmRes, res_bar(ew, buf ^ 1), n0 + 64, r0, rb);
+                            // the patch the previous chunk was stored from takes the residual of chunk ci - 1 + NP
+                            if (lane == 0 && ci >= 1 && ci - 1 + NP < NCI && n0 + (NP - 1) * 64 < p.N) {
+                                const int pb = (ci - 1) % NP;
+                                ptx::bulk_wait_read<0>();  // that store no longer reads the patch
+                                ptx::mbar_expect_tx(res_bar(ew, pb), STG_BYTES);
+                                ptx::tma_load_3d(stg + (uint32_t)(pb * STG_BYTES), &tmRes, res_bar(ew, pb), n0 + (NP - 1) * 64, r0, rb);
                             }
                             ptx::mbar_wait(res_bar(ew, buf), (rphase >> buf) & 1u);
                             rphase ^= 1u << buf;
@@ -370,6 +526,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
                             }
                             *sp = make_float4(v[0], v[1], v[2], v[3]);
+                            if (ln_out) {  // keep the finished values: statistics and the bf16 copy follow the store
+                                acc[4 * j + 0] = __float_as_uint(v[0]); acc[4 * j + 1] = __float_as_uint(v[1]);
+                                acc[4 * j + 2] = __float_as_uint(v[2]); acc[4 * j + 3] = __float_as_uint(v[3]);
+                            }
                         }
                         ptx::fence_proxy_async();
                         __syncwarp();
@@ -377,7 +537,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ptx::tma_store_3d(&tmOut, sb, n0, r0, b);
                             ptx::bulk_commit();
                         }
+                        if (ln_out) {
+                            if (!(p.debug & 16)) ln_stats_chunk(acc, ln_cnt, ln_mean, ln_m2);
+                            if (p.debug & 8) {
+                            } else if (p.debug & 32) {
+                                if (r0 + lane < p.rows_per_batch) ln_store_bf16_row(acc, e.xb_out + (long long)b * e.out_bs + (long long)(r0 + lane) * e.ldo + n0);
+                            } else {
+                                const int qr = r0 + (lane & ~3);  // first row of this lane's quad
+                                ln_store_bf16_chunk(acc, e.xb_out + (long long)b * e.out_bs + (long long)qr * e.ldo + n0, e.ldo, lane, p.rows_per_batch - qr);
+                            }
+                        }
                     }
+                    // one partial per (row, n tile, epilogue warp group); the consuming GEMM's statistics warp merges a row's slots
+                    if (ln_out && r0 + lane < p.rows_per_batch)
+                        e.stats_out[(long long)(n_idx * 2 + grp) * e.stats_ld + (long long)b * p.rows_per_batch + r0 + lane] = make_float2(ln_mean, ln_m2);
                 }
             } else {
                 // ---------- direct thread-per-row epilogue (unaligned shapes; also the no-memory microbenchmark mode) ----------
@@ -453,13 +626,13 @@ int tmap_encode(nb200_ctx *ctx, CUtensorMap *out, CUtensorMapDataType dt, const 
 }
 
 // cluster launch of the paired kernel (the cluster shape is a launch attribute, so one kernel template serves both)
-template <int BN>
+template <int BN, int NP>
 cudaError_t launch_pair(int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const CUtensorMap &r,
                         const GemmTcParams &p) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN, true>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = GemmCfg<BN, true, NP>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -468,7 +641,7 @@ cudaError_t launch_pair(int grid, cudaStream_t st, const CUtensorMap &a, const C
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true>, a, b, o, r, p);
+    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true, NP>, a, b, o, r, p);
 }
 
 }  // namespace
@@ -479,9 +652,11 @@ int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int ran
 }
 
 int gemm_tc_init(nb200_ctx *ctx) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, false>::SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false>::SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, false, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 3>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 4>::SMEM_BYTES));
     return NB200_OK;
 }
 
@@ -496,6 +671,10 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     bool pair = mode == 2 && s.N >= 256;
     bool use128 = !pair && (mode == 3 || (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
     if (mode == 2 && (long long)s.rows_per_batch * s.batch <= 2048 && s.N <= 1536 && s.N % 128 == 0 && !ctx->opt.gemm_nofit) {
+        pair = false;
+        use128 = true;
+    }
+    if (e.stats_out && s.N % 256 != 0 && s.N % 128 == 0) {  // fused LayerNorm statistics are per whole n tile
         pair = false;
         use128 = true;
     }
@@ -517,6 +696,14 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     // the TMA epilogue handles (bf16 out, no residual) and (f32 out, optional f32 residual) on 16-byte aligned rows
     p.use_tma = epi == 1 && p.vec_ok && !(e.out_bf16 && e.residual) && e.ldo > 0;
     p.res_b0 = (e.residual && (s.batch == 1 || e.res_bs == 0)) ? 1 : 0;
+    if (e.stats_out) {  // fused LayerNorm, producer: whole tiles only, one slot per (n tile, epilogue warp group)
+        if (!p.use_tma || e.out_bf16 || !e.xb_out || s.N % BN != 0 || p.n_tiles * 2 > LN_MAX_SLOTS || e.ldo % 16 != 0 || ((uintptr_t)e.xb_out & 31))
+            return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "gemm_bf16: fused LayerNorm statistics need f32 TMA output and N %% %d == 0 (N=%d)", BN, s.N);
+        ctx->ln_slots = p.n_tiles * 2;
+        ctx->ln_slot_cols = BN / 2;
+    }
+    if (e.stats_in && (!p.use_tma || !e.out_bf16 || e.stats_slots <= 0 || e.stats_slots > LN_MAX_SLOTS))
+        return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "gemm_bf16: fused LayerNorm input needs bf16 TMA output (N=%d)", s.N);
 
     CUtensorMap tmA, tmB, tmOut, tmRes;
     {
@@ -553,11 +740,15 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     if (pair) {
         const int max_cl = ctx->sm_count / 2;
         const int clusters = p.total_tiles < max_cl ? p.total_tiles : max_cl;
-        CUDA_TRY(ctx, launch_pair<256>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p));
+        // f32 residual: three (NB200_GEMM_NP=4: four) residual loads in flight per epilogue warp, paid for with pipeline stages
+        const int np = (e.residual && !e.out_bf16 && p.use_tma) ? ctx->opt.gemm_np : 2;
+        if (np == 4) CUDA_TRY(ctx, (launch_pair<256, 4>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
+        else if (np == 3) CUDA_TRY(ctx, (launch_pair<256, 3>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
+        else CUDA_TRY(ctx, (launch_pair<256, 2>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
     } else {
         const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-        if (BN == 256) gemm_tc_kernel<256, false><<<grid, GEMM_THREADS, GemmCfg<256, false>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
-        else gemm_tc_kernel<128, false><<<grid, GEMM_THREADS, GemmCfg<128, false>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
+        if (BN == 256) gemm_tc_kernel<256, false, 2><<<grid, GEMM_THREADS, GemmCfg<256, false, 2>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
+        else gemm_tc_kernel<128, false, 2><<<grid, GEMM_THREADS, GemmCfg<128, false, 2>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;

@@ -250,3 +250,35 @@ def test_streaming_bit_identity_distil_large_v3_shape(lib):
     assert np.array_equal(mel, batch_mel(pcm[drain:]))
     assert np.array_equal(feat, ctx.transcode_batch(pcm[None, drain:].copy())[0])
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ (e) LayerNorm folded into the GEMMs
+@pytest.mark.parametrize("name,shift", [("tiny.en", 0.0), ("base.en", 0.0), ("base.en", 1.5)])
+def test_layernorm_fold_matches_standalone_layernorm_and_oracle(lib, monkeypatch, name, shift):
+    """bf16 encoder with the LayerNorms folded into the QKV / fc1 GEMMs (default) against (a) the same context with standalone LayerNorm
+    kernels (NB200_LN_FUSED=0) and (b) the oracle: both within the north-star 1e-2.  `shift` moves every residual-stream row off zero mean
+    (conv2 bias + shift: row mean ~ shift against a row std of ~1), the case where x . W'^T - mean . (W' . 1) has something to cancel."""
+    c = synth.model_config(name)
+    w = synth.synth_weights(c, seed=2, decoder=False)
+    w["model.encoder.conv2.bias"] = w["model.encoder.conv2.bias"] + shift
+    f = filters.mel_filters(c["num_mel_bins"])
+    pcm = np.stack([synth.synth_pcm("gauss", 5), synth.synth_pcm("uniform", 6), synth.synth_pcm("bursts", 7)])
+    mel = np.stack([mel_c.pcm_to_mel(p, f)[:, :3000] for p in pcm])
+    ref = WhisperOracle(Config(**c), w).encoder_forward(torch.from_numpy(mel)).numpy()
+    got = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("NB200_LN_FUSED", fused)
+        ctx = ffi.Context(c, compute="bf16", max_batch=3)
+        ctx.set_mel_filters(f)
+        ctx.load_weights(w)
+        l0 = ctx.query("kernel_launches")
+        got[fused] = ctx.transcode_batch(pcm)
+        got[fused + "n"] = ctx.query("kernel_launches") - l0
+        one = ctx.transcode_batch(pcm[1:2].copy())  # one window: the 128 x 128 tile configuration writes 2 x d/128 partial slots
+        assert rel_fro(one[0], got[fused][1]) <= 2e-3
+        ctx.close()
+    r1, r0, rr = rel_fro(got["1"], ref), rel_fro(got["0"], ref), rel_fro(got["1"], got["0"])
+    print(f"{name} shift {shift}: folded vs oracle {r1:.3e}, standalone vs oracle {r0:.3e}, folded vs standalone {rr:.3e}; launches {got['1n']} vs {got['0n']}")
+    assert r1 <= 1e-2 and r0 <= 1e-2
+    assert r1 <= 1.5 * r0 + 1e-3  # folding must not cost accuracy
+    assert got["0n"] - got["1n"] == 2 * c["encoder_layers"]  # every LayerNorm but ln_post is gone
