@@ -477,7 +477,7 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
         auto env = [](const char *k) { return getenv(k); };
         auto is = [&](const char *k, const char *v) { const char *e = env(k); return e && !strcmp(e, v); };
         CtxOptions &o = ctx->opt;
-        o.gemm_mode = is("NB200_GEMM", "1cta") ? 1 : is("NB200_GEMM", "1cta128") ? 3 : 2;
+        o.gemm_mode = is("NB200_GEMM", "1cta") ? 1 : is("NB200_GEMM", "1cta128") ? 3 : is("NB200_GEMM", "2cta128") ? 4 : 2;
         o.gemm_epi_tma = is("NB200_EPI", "direct") ? 0 : 1;
         o.gemm_nofit = env("NB200_GEMM_NOFIT") != nullptr;
         o.gemm_debug = env("NB200_GEMM_DEBUG") ? atoi(env("NB200_GEMM_DEBUG")) : 0;
@@ -486,6 +486,7 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
         o.decode_fused = (env("NB200_DECODE_FUSED") && env("NB200_DECODE_FUSED")[0] == '0') ? 0 : 1;
         o.decode_graph = env("NB200_DECODE_NOGRAPH") ? 0 : 1;
         o.encoder_graph = env("NB200_ENCODER_NOGRAPH") ? 0 : 1;
+        if (env("NB200_PDL")) o.pdl = atoi(env("NB200_PDL"));
         o.ln_fused = (env("NB200_LN_FUSED") && env("NB200_LN_FUSED")[0] == '0') ? 0 : 1;
         o.prof_dump = env("NB200_PROF_DUMP") != nullptr;
     }

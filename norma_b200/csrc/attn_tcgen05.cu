@@ -204,6 +204,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t tO = tmem_base + NS * 64;
+    ptx::griddep_wait();  // q | k | v come from the previous kernel; the set-up above overlapped its tail
+    ptx::griddep_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -368,7 +370,7 @@ int launch_attention_tc(nb200_ctx *ctx, const bf16 *qkv, bf16 *out, int B, int T
     cudaMemsetAsync(dbg_buf, 0, 128, ctx->stream);
     dbg = dbg_buf;
 #endif
-    attn_tc_kernel<<<ctas, AT_THREADS, AtCfg::SMEM, ctx->stream>>>(tq, tkv, out, T, d, n_heads, n_items, dbg);
+    CUDA_TRY(ctx, launch_chain(ctx, 2, attn_tc_kernel, dim3(ctas), dim3(AT_THREADS), AtCfg::SMEM, 1, tq, tkv, out, T, d, n_heads, n_items, dbg));
     CUDA_TRY(ctx, cudaGetLastError());
 #ifdef NB200_ATTN_TIMING  // scripts/probes: where a softmax warp's cycles go (clock64 deltas kept in registers, one atomicAdd per warp at the end)
     {

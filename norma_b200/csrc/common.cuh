@@ -89,6 +89,9 @@ struct CtxOptions {
     int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels
     int decode_graph = 1;     // NB200_DECODE_NOGRAPH -> 0
     int encoder_graph = 1;    // NB200_ENCODER_NOGRAPH -> 0: launch the encoder kernel by kernel
+    int pdl = 0;              // NB200_PDL: bit mask of the kernels launched with programmatic dependent launch (1 GEMM, 2 attention, 4 LayerNorm);
+                              // off: measured 3.702 vs 3.719 ms per window (kernels of the chain own their SM, only prologues overlap) and,
+                              // with the folded LayerNorm, the streaming path lost its bit-identity with the one-shot path (profiles/r2_notes.md)
     int ln_fused = 1;         // NB200_LN_FUSED=0 -> standalone LayerNorm kernels in the encoder
     int prof_dump = 0;        // NB200_PROF_DUMP
 };
@@ -292,6 +295,34 @@ int decoder_init_state(nb200_ctx *ctx, int n_windows);
 int encoder_run(nb200_ctx *ctx, int n_windows);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Launch of a kernel on the encoder chain: optional cluster shape, and (ctx->opt.pdl) programmatic dependent launch, so the kernel's
+// prologue overlaps the tail of its predecessor.  ONLY for kernels that execute ptx::griddep_wait() before their first global access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(nb200_ctx *ctx, int pdl_bit, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_x, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (ctx->opt.pdl & pdl_bit) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 static inline size_t dtype_size(nb200_dtype t) { return t == NB200_F32 ? 4 : 2; }
 
 // tanh-approximation GELU exactly as candle's `Tensor::gelu`

@@ -1085,18 +1085,24 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
                 const unsigned ct = cnt + warp, st = ct % FS_STAGES;
                 ptx::mbar_wait(full0 + 8 * st, (ct / FS_STAGES) & 1);
                 const uint32_t arow = ring + st * FS_TILE_BYTES + (lane & 15) * pitch + (lane >> 4) * 16;
-#pragma unroll 4
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                    uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
-                    if (bn < Bd) {
-                        b0 = *(const uint32_t *)(xk + ks * 16);
-                        b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+                // four k-steps per trip with the accumulator index a compile-time constant (d_model is a multiple of 64): with `acc[ks & 3]` in
+                // a partially unrolled loop the remainder loop indexed the fragments dynamically and ptxas put all sixteen accumulators in
+                // local memory — every mma.sync of the step sat between an LDL and an STL (ncu: 14 M local loads per 16 positions)
+#pragma unroll 1
+                for (int k4 = 0; k4 < KC / 64; ++k4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ks = k4 * 4 + u;
+                        uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
+                        if (bn < Bd) {
+                            b0 = *(const uint32_t *)(xk + ks * 16);
+                            b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+                        }
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                     : "+f"(acc[u][0]), "+f"(acc[u][1]), "+f"(acc[u][2]), "+f"(acc[u][3])
+                                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
                     }
-                    float *dd = acc[ks & 3];
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                                 : "+f"(dd[0]), "+f"(dd[1]), "+f"(dd[2]), "+f"(dd[3])
-                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(empty0 + 8 * st);
@@ -1152,18 +1158,21 @@ __device__ __noinline__ void fs_gemv(const FusedArgs &a, int j, const float *x, 
                 ptx::mbar_wait(full0 + 8 * s, (cnt / FS_STAGES) & 1);
                 const uint32_t arow = ring + s * FS_TILE_BYTES + (lane & 15) * pitch + (lane >> 4) * 16;
                 const bf16 *xk = xrow + c * KC;
-#pragma unroll 4
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                    uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
-                    if (bn < Bd) {
-                        b0 = *(const uint32_t *)(xk + ks * 16);
-                        b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+#pragma unroll 1
+                for (int k4 = 0; k4 < KC / 64; ++k4) {  // accumulator index static, see above
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ks = k4 * 4 + u;
+                        uint32_t a0, a1, a2, a3, b0 = 0u, b1 = 0u;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(arow + ks * 32));
+                        if (bn < Bd) {
+                            b0 = *(const uint32_t *)(xk + ks * 16);
+                            b1 = *(const uint32_t *)(xk + ks * 16 + 8);
+                        }
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                                     : "+f"(acc[u][0]), "+f"(acc[u][1]), "+f"(acc[u][2]), "+f"(acc[u][3])
+                                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
                     }
-                    float *d = acc[ks & 3];
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(empty0 + 8 * s);  // the tile has been read: the stage can be refilled

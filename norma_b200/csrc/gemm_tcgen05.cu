@@ -278,6 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const int k_blocks = (p.debug & 2) ? 0 : p.k_blocks;
+    ptx::griddep_wait();    // everything above overlapped the previous kernel's tail; from here on its results are needed
+    ptx::griddep_launch();  // AFTER the wait: the next kernel's CTAs may take this SM as soon as this CTA leaves it, but never start while the
+                            // kernel before this one still runs (a trigger in front of the wait let three kernels overlap and broke bit-identity)
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -625,25 +628,6 @@ int tmap_encode(nb200_ctx *ctx, CUtensorMap *out, CUtensorMapDataType dt, const 
     return NB200_OK;
 }
 
-// cluster launch of the paired kernel (the cluster shape is a launch attribute, so one kernel template serves both)
-template <int BN, int NP>
-cudaError_t launch_pair(int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &o, const CUtensorMap &r,
-                        const GemmTcParams &p) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GemmCfg<BN, true, NP>::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true, NP>, a, b, o, r, p);
-}
-
 }  // namespace
 
 int tmap_encode_bf16(nb200_ctx *ctx, CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
@@ -655,6 +639,7 @@ int gemm_tc_init(nb200_ctx *ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, false, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, true, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 3>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 4>::SMEM_BYTES));
     return NB200_OK;
@@ -668,13 +653,13 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     // Tile configuration: the CTA-pair 256 x 256 tile wins everywhere except for ONE window's worth of rows (streaming, BASELINE configs 4 / 5 at
     // B = 1) on the N = d_model GEMMs, where 6 x 5 pair tiles occupy 30 of 74 pairs; 128 x 128 single-CTA tiles (120 of 148 CTAs) are then
     // faster (scripts/gpu_gemm_fit.py, M = 1500: out-proj 18.6 -> 14.4 us, fc2 36.5 -> 28.5 us; from M = 3000 on the pair tile is as fast or faster)
-    bool pair = mode == 2 && s.N >= 256;
-    bool use128 = !pair && (mode == 3 || (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128);
+    bool pair = (mode == 2 && s.N >= 256) || (mode == 4 && s.N >= 128);
+    bool use128 = mode == 4 ? pair : (!pair && (mode == 3 || (s.N % 256 != 0 && s.N % 128 == 0 && s.N <= 1024) || s.N <= 128));
     if (mode == 2 && (long long)s.rows_per_batch * s.batch <= 2048 && s.N <= 1536 && s.N % 128 == 0 && !ctx->opt.gemm_nofit) {
         pair = false;
         use128 = true;
     }
-    if (e.stats_out && s.N % 256 != 0 && s.N % 128 == 0) {  // fused LayerNorm statistics are per whole n tile
+    if (e.stats_out && s.N % 256 != 0 && s.N % 128 == 0 && !use128) {  // fused LayerNorm statistics are per whole n tile
         pair = false;
         use128 = true;
     }
@@ -715,7 +700,7 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     {
         uint64_t dims[2] = {(uint64_t)s.K, (uint64_t)s.N};
         uint64_t str[1] = {(uint64_t)s.K * 2};
-        uint32_t box[2] = {BK, (uint32_t)(pair ? BN / 2 : BN)};
+        uint32_t box[2] = {BK, (uint32_t)(pair ? BN / 2 : BN)};  // a CTA of a pair loads half of the W tile
         NB_TRY(tmap_encode_bf16(ctx, &tmB, W, 2, dims, str, box));
     }
     tmOut = tmA;
@@ -742,13 +727,14 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
         const int clusters = p.total_tiles < max_cl ? p.total_tiles : max_cl;
         // f32 residual: three (NB200_GEMM_NP=4: four) residual loads in flight per epilogue warp, paid for with pipeline stages
         const int np = (e.residual && !e.out_bf16 && p.use_tma) ? ctx->opt.gemm_np : 2;
-        if (np == 4) CUDA_TRY(ctx, (launch_pair<256, 4>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
-        else if (np == 3) CUDA_TRY(ctx, (launch_pair<256, 3>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
-        else CUDA_TRY(ctx, (launch_pair<256, 2>(2 * clusters, ctx->stream, tmA, tmB, tmOut, tmRes, p)));
+        if (BN == 128) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<128, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<128, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
+        else if (np == 4) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 4>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 4>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
+        else if (np == 3) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 3>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 3>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
+        else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
     } else {
         const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
-        if (BN == 256) gemm_tc_kernel<256, false, 2><<<grid, GEMM_THREADS, GemmCfg<256, false, 2>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
-        else gemm_tc_kernel<128, false, 2><<<grid, GEMM_THREADS, GemmCfg<128, false, 2>::SMEM_BYTES, ctx->stream>>>(tmA, tmB, tmOut, tmRes, p);
+        if (BN == 256) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, false, 2>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<256, false, 2>::SMEM_BYTES, 1, tmA, tmB, tmOut, tmRes, p));
+        else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<128, false, 2>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<128, false, 2>::SMEM_BYTES, 1, tmA, tmB, tmOut, tmRes, p));
     }
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float *__restrict__ x, const float *__restrict__ g, const float *__restrict__ bta, int rows, int d,
                  OutT *__restrict__ out, float *__restrict__ out2) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // programmatic dependent launch (common.cuh launch_chain): x comes from the previous kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp >= rows) return;
     const int nch = d >> 7;  // float4 chunks per lane
     const float4 *xr = (const float4 *)(x + (size_t)warp * d);
@@ -307,8 +309,8 @@ int launch_layernorm(nb200_ctx *ctx, const float *x, const float *g, const float
     if (d % 128 != 0 || d > 1280) return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "layernorm: d=%d (need d %% 128 == 0, d <= 1280)", d);
     KernelScope ks(ctx, NB200_K_LAYERNORM);
     int blocks = ceil_div(rows, 8);
-    if (out_bf16) layernorm_kernel<bf16><<<blocks, 256, 0, ctx->stream>>>(x, g, b, rows, d, (bf16 *)out, out2_f32);
-    else layernorm_kernel<float><<<blocks, 256, 0, ctx->stream>>>(x, g, b, rows, d, (float *)out, out2_f32);
+    if (out_bf16) CUDA_TRY(ctx, launch_chain(ctx, 4, layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, 1, x, g, b, rows, d, (bf16 *)out, out2_f32));
+    else CUDA_TRY(ctx, launch_chain(ctx, 4, layernorm_kernel<float>, dim3(blocks), dim3(256), 0, 1, x, g, b, rows, d, (float *)out, out2_f32));
     CUDA_TRY(ctx, cudaGetLastError());
     return NB200_OK;
 }
