@@ -84,7 +84,7 @@ struct CtxOptions {
     int gemm_epi_tma = 1;     // NB200_EPI=direct -> 0: thread-per-row stores
     int gemm_nofit = 0;       // NB200_GEMM_NOFIT: keep the pair tile for one window's worth of rows
     int gemm_debug = 0;       // NB200_GEMM_DEBUG: microbenchmark switches of gemm_tc_kernel
-    int gemm_np = 2;          // NB200_GEMM_NP: staging patches per epilogue warp of the f32-residual GEMMs (2, 3 or 4)
+    int gemm_wide = 1;        // NB200_GEMM_WIDE=0: no single-round wide tiles for one window's worth of rows (gemm_wide_kernel)
     int attn_tc = 1;          // NB200_ATTN=simt -> 0: CUDA-core attention
     int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels
     int decode_graph = 1;     // NB200_DECODE_NOGRAPH -> 0

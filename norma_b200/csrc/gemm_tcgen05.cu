@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <vector>
 
 namespace {
 
@@ -40,6 +41,7 @@ struct GemmTcParams {
     int use_tma;  // TMA-store epilogue (needs 16-byte aligned rows); 0 = direct thread-per-row stores
     int res_b0;   // residual has no batch dimension (positional table): always batch coordinate 0
     int debug;    // microbenchmark switches: 1 = epilogue touches no global memory, 2 = no TMA / MMA mainloop
+    long long *dbg_clk;  // NB200_GEMM_DEBUG & 256 (gemm_wide_kernel): per-CTA clock64 stamps of the phases, [grid][8]
     Epilogue epi;
 };
 
@@ -54,14 +56,16 @@ struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING = EPI_WARPS * NP * STG_BYTES;
-    static constexpr int BAR_BYTES = 512;
-    static constexpr int LN_BYTES = 2 * BM * 4;  // 1 / std of the tile's rows, per accumulator stage (fused LayerNorm consumer)
-    static constexpr int SMEM_LIMIT = 232448;  // the 227 KB a CTA may opt in to
-    static constexpr int FIT = (SMEM_LIMIT - STAGING - 1024 - BAR_BYTES - LN_BYTES) / STAGE_BYTES;
+    static constexpr int BAR_BYTES = 320;
+    static constexpr int LN_BYTES = BM * 4;        // 1 / std of the tile's rows (fused LayerNorm consumer)
+    static constexpr int BIAS_BYTES = 2 * BN * 4;  // the tile's bias, per accumulator stage
+    static constexpr int SMEM_LIMIT = 232448;      // the 227 KB a CTA may opt in to
+    static constexpr int FIT = (SMEM_LIMIT - STAGING - BAR_BYTES - LN_BYTES - BIAS_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = FIT > 5 ? 5 : FIT;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int TILE_M = CTA2 ? 256 : 128;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + BAR_BYTES + LN_BYTES;
+    // no alignment slack: the dynamic shared memory of a kernel without static shared memory starts 1024-byte aligned (checked, trap)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + LN_BYTES + BIAS_BYTES;
     static_assert(STAGES >= 3, "pipeline too shallow");
     static_assert((2 * STAGES + 9 + EPI_WARPS * NP) * 8 <= BAR_BYTES, "barrier block");
     static_assert(SMEM_BYTES <= SMEM_LIMIT, "exceeds the 227 KB of shared memory a CTA may opt in to");
@@ -206,9 +210,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                const __grid_constant__ CUtensorMap tmRes, const GemmTcParams p) {
     using C = GemmCfg<BN, CTA2, NP>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_raw_u = ptx::smem_u32(smem_raw);
-    const uint32_t smem_base = (smem_raw_u + 1023u) & ~1023u;
+    if (threadIdx.x == 0 && (smem_raw_u & 1023u)) __trap();  // the swizzled tiles need it; there is no slack to align by hand
+    const uint32_t smem_base = smem_raw_u;
     const uint32_t sA = smem_base, sB = smem_base + C::STAGES * C::A_BYTES;
     const uint32_t stg_base = smem_base + C::STAGES * C::STAGE_BYTES;  // 1024-aligned
     const uint32_t bars = stg_base + C::STAGING;
@@ -222,7 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // fused LayerNorm (consumer): warp 3 merges the rows' partial statistics of every tile and publishes 1 / std per accumulator stage
     auto lnfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 5 + NP * EPI_WARPS + s); };
     auto lnempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 7 + NP * EPI_WARPS + s); };
-    float *ln_smem = (float *)(smem_raw + (bars + C::BAR_BYTES - smem_raw_u));  // [2][BM]
+    float *ln_smem = (float *)(smem_raw + (bars + C::BAR_BYTES - smem_raw_u));  // [BM]
+    // the tile's bias, staged once per tile by the epilogue warps while the mainloop runs: bias loads straight from global memory inside the
+    // chunk loop were one L2 round trip per 8 columns, in program order (4 800 clk of a 64-column chunk's 5 000, measured with clock64)
+    float *bias_smem = ln_smem + BM;  // [2][BN]
     volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_raw_u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int t = 0; tile_at(t, mb, n_idx); ++t) {
                 const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
                 const int r0 = mt * C::TILE_M + (int)rank * BM;
-                ptx::mbar_wait(lnempty_bar(as), aphase ^ 1u);
+                ptx::mbar_wait(lnempty_bar(0), (uint32_t)(t & 1) ^ 1u);  // the epilogue warps hold the previous tile's values in registers
                 const float2 *sp = e.stats_in + (long long)b * p.rows_per_batch + r0 + lane;
                 float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
                 bool ok[4];
@@ -374,9 +382,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     cnt = tot;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ln_smem[as * BM + lane + 32 * k] = rsqrtf(m2[k] / cnt + LN_EPS);
+                for (int k = 0; k < 4; ++k) ln_smem[lane + 32 * k] = rsqrtf(m2[k] / cnt + LN_EPS);
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(lnfull_bar(as));  // release: the stores above are ordered before the arrival
+                if (lane == 0) ptx::mbar_arrive(lnfull_bar(0));  // release: the stores above are ordered before the arrival
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
@@ -402,6 +410,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nt0 = n_idx * BN;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             const int rb = p.res_b0 ? 0 : b;
+            // the tile's bias -> shared memory (all 8 epilogue warps, one L2 round trip in the shadow of the mainloop).  The named barrier also
+            // orders the reuse of the buffer two tiles on: every warp has finished tile t - 1, so nobody still reads tile t - 2's values.
+            float *bs = bias_smem + as * BN;
+            for (int k = ew * 32 + lane; k < BN; k += 32 * EPI_WARPS) bs[k] = (e.bias && nt0 + k < p.N) ? __ldg(e.bias + nt0 + k) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             if (p.use_tma && !no_mem) {
                 if (e.out_bf16) {
                     // ---------- bf16 out: 64-column chunks (128 B rows), no residual ----------
@@ -409,10 +422,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // (W . diag(gamma) . (I - 11^T / K)), so all that is left of the LayerNorm is this row's 1 / std
                     float ln_rstd = 1.0f;
                     if (e.stats_in != nullptr) {  // published by the statistics warp (warp 3) for this accumulator stage
-                        ptx::mbar_wait(lnfull_bar(as), aphase);
-                        ln_rstd = ln_smem[as * BM + q * 32 + lane];
+                        ptx::mbar_wait(lnfull_bar(0), (uint32_t)(t & 1));
+                        ln_rstd = ln_smem[q * 32 + lane];
                         __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(lnempty_bar(as));
+                        if (lane == 0) ptx::mbar_arrive(lnempty_bar(0));
                     }
                     ptx::mbar_wait(tfull_bar(as), aphase);
                     ptx::tc_fence_after();
@@ -434,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [8j, 8j+8)
-                            const float4 b0 = bias4(e, n0 + 8 * j, p.N, full), b1 = bias4(e, n0 + 8 * j + 4, p.N, full);
+                            const float4 b0 = *(const float4 *)(bs + c * 64 + 8 * j), b1 = *(const float4 *)(bs + c * 64 + 8 * j + 4);
                             float v[8];
                             v[0] = fmaf(__uint_as_float(acc[8 * j + 0]), ln_rstd, b0.x) * cs; v[1] = fmaf(__uint_as_float(acc[8 * j + 1]), ln_rstd, b0.y) * cs;
                             v[2] = fmaf(__uint_as_float(acc[8 * j + 2]), ln_rstd, b0.z) * cs; v[3] = fmaf(__uint_as_float(acc[8 * j + 3]), ln_rstd, b0.w) * cs;
@@ -510,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [4j, 4j+4)
-                            const float4 bb = bias4(e, n0 + 4 * j, p.N, full);
+                            const float4 bb = *(const float4 *)(bs + c * 32 + 4 * j);
                             float v[4];
                             v[0] = (__uint_as_float(acc[4 * j + 0]) + bb.x) * cs; v[1] = (__uint_as_float(acc[4 * j + 1]) + bb.y) * cs;
                             v[2] = (__uint_as_float(acc[4 * j + 2]) + bb.z) * cs; v[3] = (__uint_as_float(acc[4 * j + 3]) + bb.w) * cs;
@@ -591,6 +604,239 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// =====================================================================================================================
+// gemm_wide_kernel — the bf16-out GEMMs (QKV, fc1) for ONE window's worth of rows (M <= 1536: BASELINE config 2 as written, streaming).
+// With 256 x 256 tiles, M = 1500 is 6 x 15 (QKV) or 6 x 20 (fc1) tiles on 74 CTA pairs: two rounds, the second nearly empty, and
+// every round pays a pipeline fill and an epilogue (22.7 / 26.0 us against 10.4 / 13.9 us of tensor time).  Here every CTA pair computes
+// exactly ONE 256 x BN tile, BN = NSUB x UN chosen so that 6 x ceil(N / BN) <= 74 pairs: one round.
+//   * BN up to 448 columns: NSUB UMMAs (256 x UN x 16, cta_group::2) per k-step into one TMEM accumulator (no double buffer: one tile);
+//   * one tile per CTA means the epilogue never overlaps a mainloop, so its staging patches ALIAS the first pipeline stages and the ring
+//     gets the whole shared memory (6 stages of 36 KB at BN = 320, 5 of 44 KB at BN = 448 — the loop is bound by bytes in flight);
+//   * same fused epilogue as gemm_tc_kernel's bf16 branch (bias, q/k scale, GELU, folded-LayerNorm 1/std from the statistics warp).
+// =====================================================================================================================
+template <int UN, int NSUB>
+struct WideCfg {
+    static constexpr int BN = UN * NSUB;
+    static constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows
+    static constexpr int B_SUB_BYTES = (UN / 2) * BK * 2;  // this CTA's half of one UMMA's W rows
+    static constexpr int B_BYTES = NSUB * B_SUB_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int LN_BYTES = BM * 4;
+    static constexpr int SMEM_LIMIT = 232448;
+    static constexpr int BIAS_BYTES = BN * 4;
+    static constexpr int STAGES = (SMEM_LIMIT - 1024 - BAR_BYTES - LN_BYTES - BIAS_BYTES) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + LN_BYTES + BIAS_BYTES;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(UN % 16 == 0 && UN <= 256 && BN <= 512, "UMMA shape");
+    static_assert(B_SUB_BYTES % 1024 == 0, "sub-tiles start on a swizzle atom");
+    static_assert(STAGES * A_BYTES >= EPI_WARPS * 2 * STG_BYTES, "the epilogue patches alias the A stages");
+    static_assert((2 * STAGES + 3) * 8 + 4 <= BAR_BYTES, "barrier block");
+};
+
+template <int UN, int NSUB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const GemmTcParams p) {
+    using C = WideCfg<UN, NSUB>;
+    constexpr int BN = C::BN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_raw_u = ptx::smem_u32(smem_raw);
+    const uint32_t smem_base = (smem_raw_u + 1023u) & ~1023u;
+    const uint32_t sA = smem_base, sB = smem_base + C::STAGES * C::A_BYTES;
+    const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+    const uint32_t tfull_bar = bars + 8u * (2 * C::STAGES), lnfull_bar = bars + 8u * (2 * C::STAGES + 1);
+    const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 2);
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_raw_u));
+    float *ln_smem = (float *)(smem_raw + (bars + C::BAR_BYTES - smem_raw_u));
+    float *bias_smem = ln_smem + BM;  // the tile's bias, staged while the mainloop runs
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int tile = (int)(blockIdx.x >> 1);
+    const int n_idx = tile % p.n_tiles, mt = tile / p.n_tiles;  // batch == 1 on this path
+    const Epilogue &e = p.epi;
+    long long *dbg = p.dbg_clk ? p.dbg_clk + (size_t)blockIdx.x * 16 : nullptr;  // phase stamps (timing build of the launch, not the product path)
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA);
+        ptx::prefetch_tmap(&tmB);
+        ptx::prefetch_tmap(&tmOut);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        ptx::mbar_init(tfull_bar, 1);
+        ptx::mbar_init(lnfull_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    ptx::griddep_wait();
+    ptx::griddep_launch();
+    if (dbg && threadIdx.x == 0) dbg[1] = clock64();  // set-up done
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+                const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                ptx::tma_load_3d_2sm(sA + stage * C::A_BYTES, &tmA, lead_full, kb * BK, mt * 256 + (int)rank * BM, 0);
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j)  // W rows of UMMA j: this CTA's half (rows beyond N arrive as zeros)
+                    ptx::tma_load_2d_2sm(sB + stage * C::B_BYTES + j * C::B_SUB_BYTES, &tmB, lead_full, kb * BK, n_idx * BN + j * UN + (int)rank * (UN / 2));
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16(256, UN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                ptx::mbar_wait(full_bar(stage), phase);
+                ptx::tc_fence_after();
+                if (dbg && kb == 0) dbg[2] = clock64();  // first operands have landed
+                if (dbg && kb == p.k_blocks - 1) dbg[3] = clock64();  // last operands have landed
+                const uint64_t da = ptx::make_sw128_desc(sA + stage * C::A_BYTES, 16, 1024);
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j) {
+                    const uint64_t db = ptx::make_sw128_desc(sB + stage * C::B_BYTES + j * C::B_SUB_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        ptx::mma_bf16_ss_2sm(tmem_base + (uint32_t)(j * UN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                ptx::mma_commit_2sm_mc(empty_bar(stage), 3);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+            ptx::mma_commit_2sm_mc(tfull_bar, 3);
+        }
+    } else if (warp == 3) {
+        // folded LayerNorm: 1 / std of this CTA's 128 rows from the producer's partial slots (as in gemm_tc_kernel)
+        if (e.stats_in != nullptr) {
+            const int r0 = mt * 256 + (int)rank * BM;
+            const float cols = (float)e.stats_cols;
+            const float2 *sp = e.stats_in + r0 + lane;
+            float cnt = 0.f, mean[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+            bool ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ok[k] = r0 + lane + 32 * k < p.rows_per_batch;
+#pragma unroll 2
+            for (int i = 0; i < e.stats_slots; ++i) {
+                float2 pm[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pm[k] = ok[k] ? __ldcg(sp + (long long)i * e.stats_ld + 32 * k) : make_float2(0.f, 1.f);
+                const float tot = cnt + cols, w = __fdividef(cols, tot);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float delta = pm[k].x - mean[k];
+                    mean[k] = fmaf(delta, w, mean[k]);
+                    m2[k] += pm[k].y + delta * delta * cnt * w;
+                }
+                cnt = tot;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ln_smem[lane + 32 * k] = rsqrtf(m2[k] / cnt + LN_EPS);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(lnfull_bar);
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4, q = warp & 3, grp = ew >> 2;
+        const uint32_t stg = sA + (uint32_t)(ew * 2 * STG_BYTES);  // aliases the A stages: nothing reads them once the accumulator is complete
+        uint8_t *stg_ptr = smem_raw + (stg - smem_raw_u);
+        const int sw = lane & 7;
+        const int r0 = mt * 256 + (int)rank * BM + q * 32;
+        const int nt0 = n_idx * BN;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int k = ew * 32 + lane; k < BN; k += 32 * EPI_WARPS) bias_smem[k] = (e.bias && nt0 + k < p.N) ? __ldg(e.bias + nt0 + k) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        float ln_rstd = 1.0f;
+        if (e.stats_in != nullptr) {
+            ptx::mbar_wait(lnfull_bar, 0);
+            ln_rstd = ln_smem[q * 32 + lane];
+        }
+        ptx::mbar_wait(tfull_bar, 0);
+        ptx::tc_fence_after();
+        if (dbg && warp == 4 && lane == 0) dbg[4] = clock64();  // accumulator complete
+        int it = 0;
+        long long e_ld = 0, e_math = 0, e_st = 0, e_n = 0;
+#pragma unroll 1
+        for (int c = grp; c < BN / 64; c += 2, ++it) {
+            const int n0 = nt0 + c * 64;
+            if (n0 >= p.N) break;  // warp-uniform
+            const uint32_t sb = stg + (uint32_t)((it & 1) * STG_BYTES);
+            uint8_t *sbp = stg_ptr + (it & 1) * STG_BYTES + lane * 128;
+            uint32_t acc[64];
+            const long long c0 = dbg ? clock64() : 0;
+            ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64), acc);
+            ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), acc + 32);
+            if (lane == 0) ptx::bulk_wait_read<1>();
+            __syncwarp();
+            const bool full = n0 + 64 <= p.N;
+            const bool mixed = n0 < e.n_scale && n0 + 64 > e.n_scale;
+            const float cs = (n0 + 64 <= e.n_scale) ? e.scale : 1.0f;
+            ptx::tmem_ld_wait();
+            const long long c1 = dbg ? clock64() : 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b0 = *(const float4 *)(bias_smem + c * 64 + 8 * j), b1 = *(const float4 *)(bias_smem + c * 64 + 8 * j + 4);
+                float v[8];
+                v[0] = fmaf(__uint_as_float(acc[8 * j + 0]), ln_rstd, b0.x) * cs; v[1] = fmaf(__uint_as_float(acc[8 * j + 1]), ln_rstd, b0.y) * cs;
+                v[2] = fmaf(__uint_as_float(acc[8 * j + 2]), ln_rstd, b0.z) * cs; v[3] = fmaf(__uint_as_float(acc[8 * j + 3]), ln_rstd, b0.w) * cs;
+                v[4] = fmaf(__uint_as_float(acc[8 * j + 4]), ln_rstd, b1.x) * cs; v[5] = fmaf(__uint_as_float(acc[8 * j + 5]), ln_rstd, b1.y) * cs;
+                v[6] = fmaf(__uint_as_float(acc[8 * j + 6]), ln_rstd, b1.z) * cs; v[7] = fmaf(__uint_as_float(acc[8 * j + 7]), ln_rstd, b1.w) * cs;
+                if (mixed) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (n0 + 8 * j + t < e.n_scale) v[t] *= e.scale;
+                }
+                if (e.act) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[t] = gelu_tanh_fast(v[t]);
+                }
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                uint4 pk;
+                pk.x = *(unsigned *)&p0; pk.y = *(unsigned *)&p1; pk.z = *(unsigned *)&p2; pk.w = *(unsigned *)&p3;
+                *(uint4 *)(sbp + ((j ^ sw) << 4)) = pk;
+            }
+            const long long c2 = dbg ? clock64() : 0;
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tmOut, sb, n0, r0, 0);  // rows beyond M and columns beyond N are clipped by the tensor map
+                ptx::bulk_commit();
+            }
+            if (dbg) { const long long c3 = clock64(); e_ld += c1 - c0; e_math += c2 - c1; e_st += c3 - c2; ++e_n; }
+        }
+        if (dbg && warp == 4 && lane == 0) { dbg[5] = clock64(); dbg[8] = e_ld; dbg[9] = e_math; dbg[10] = e_st; dbg[11] = e_n; }  // last store issued
+        if (lane == 0) ptx::bulk_wait_all();
+        if (dbg && warp == 4 && lane == 0) dbg[6] = clock64();  // stores written
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    }
+    if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -640,8 +886,8 @@ int gemm_tc_init(nb200_ctx *ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, true, 2>::SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 3>::SMEM_BYTES));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 4>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_wide_kernel<160, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<160, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_wide_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<224, 2>::SMEM_BYTES));
     return NB200_OK;
 }
 
@@ -690,6 +936,70 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     if (e.stats_in && (!p.use_tma || !e.out_bf16 || e.stats_slots <= 0 || e.stats_slots > LN_MAX_SLOTS))
         return nb200_fail(ctx, NB200_UNSUPPORTED_SHAPE, "gemm_bf16: fused LayerNorm input needs bf16 TMA output (N=%d)", s.N);
 
+    // One window's worth of rows on a wide GEMM (QKV, fc1 at d_model 1280): one 256 x BN tile per CTA pair, a single round (gemm_wide_kernel)
+    if (ctx->opt.gemm_wide && p.use_tma && e.out_bf16 && !e.residual && s.batch == 1 && s.rows_per_batch <= 1536 && s.N > 1536 && s.N % 64 == 0 &&
+        mode == 2) {
+        const int pairs = ctx->sm_count / 2, mt = ceil_div(s.rows_per_batch, 256);
+        int bn = 0;
+        for (int cand : {320, 448}) {
+            const int tiles = mt * ceil_div(s.N, cand);
+            if (tiles <= pairs && tiles * 10 >= pairs * 8) { bn = cand; break; }
+        }
+        if (bn) {
+            p.m_tiles_per_batch = mt;
+            p.n_tiles = ceil_div(s.N, bn);
+            p.total_tiles = mt * p.n_tiles;
+            CUtensorMap tmA, tmB, tmOut;
+            {
+                uint64_t dims[3] = {(uint64_t)s.K, (uint64_t)s.rows_per_batch, 1};
+                uint64_t str[2] = {(uint64_t)s.lda * 2, (uint64_t)s.lda * s.rows_per_batch * 2};
+                uint32_t box[3] = {BK, BM, 1};
+                NB_TRY(tmap_encode_bf16(ctx, &tmA, A, 3, dims, str, box));
+            }
+            {
+                uint64_t dims[2] = {(uint64_t)s.K, (uint64_t)s.N};
+                uint64_t str[1] = {(uint64_t)s.K * 2};
+                uint32_t box[2] = {BK, (uint32_t)(bn / 4)};  // UN / 2 rows: this CTA's half of one UMMA's W rows
+                NB_TRY(tmap_encode_bf16(ctx, &tmB, W, 2, dims, str, box));
+            }
+            {
+                uint64_t dims[3] = {(uint64_t)s.N, (uint64_t)s.rows_per_batch, 1};
+                uint64_t str[2] = {(uint64_t)e.ldo * 2, (uint64_t)e.ldo * s.rows_per_batch * 2};
+                uint32_t box[3] = {64, 32, 1};
+                NB_TRY(tmap_encode_bf16(ctx, &tmOut, e.out, 3, dims, str, box));
+            }
+            KernelScope ks(ctx, NB200_K_GEMM, (long long)s.N * 100000 + s.K);
+            ctx->prof_gemm_flops += 2.0 * s.rows_per_batch * (double)s.N * s.K;
+            p.dbg_clk = nullptr;
+            static thread_local long long *dbg_buf = nullptr;  // timing build of a launch only (NB200_GEMM_DEBUG & 256): never set on the product path
+            if (p.debug & 256) {
+                if (!dbg_buf) cudaMalloc(&dbg_buf, 2 * 74 * 16 * sizeof(long long));
+                p.dbg_clk = dbg_buf;
+            }
+            if (bn == 320) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_wide_kernel<160, 2>, dim3(2 * p.total_tiles), dim3(GEMM_THREADS), WideCfg<160, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, p));
+            else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_wide_kernel<224, 2>, dim3(2 * p.total_tiles), dim3(GEMM_THREADS), WideCfg<224, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, p));
+            CUDA_TRY(ctx, cudaGetLastError());
+            if (p.debug & 256) {  // where a CTA's cycles go, averaged over the grid (stderr)
+                std::vector<long long> h((size_t)2 * p.total_tiles * 16);
+                cudaStreamSynchronize(ctx->stream);
+                cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                double d[7] = {0, 0, 0, 0, 0, 0, 0}, ee[4] = {0, 0, 0, 0};
+                int nl = 0;
+                for (int c = 0; c < 2 * p.total_tiles; c += 2, ++nl) {  // leader CTAs (they own the MMA stamps)
+                    const long long *t = &h[(size_t)c * 16];
+                    d[0] += t[1] - t[0]; d[1] += t[2] - t[1]; d[2] += t[3] - t[2]; d[3] += t[4] - t[3]; d[4] += t[5] - t[4]; d[5] += t[6] - t[5]; d[6] += t[7] - t[0];
+                    ee[0] += t[8]; ee[1] += t[9]; ee[2] += t[10]; ee[3] += t[11];
+                }
+                fprintf(stderr, "   epilogue warp 4, clk per 64-column chunk: tcgen05.ld + wait %.0f | bias + math + pack + st.shared %.0f | fence + store issue %.0f (%.1f chunks)\n",
+                        ee[0] / ee[3], ee[1] / ee[3], ee[2] / ee[3], ee[3] / nl);
+                fprintf(stderr, "[gemm_wide N=%d K=%d] clk per CTA: set-up %.0f | first operands %.0f | mainloop (first -> last operands) %.0f | last operands -> accumulator "
+                                "%.0f | epilogue %.0f | store drain %.0f || whole CTA %.0f\n", s.N, s.K, d[0] / nl, d[1] / nl, d[2] / nl, d[3] / nl, d[4] / nl, d[5] / nl, d[6] / nl);
+            }
+            return NB200_OK;
+        }
+    }
+    p.dbg_clk = nullptr;
+
     CUtensorMap tmA, tmB, tmOut, tmRes;
     {
         uint64_t dims[3] = {(uint64_t)s.K, (uint64_t)s.rows_per_batch, (uint64_t)s.batch};
@@ -725,11 +1035,9 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     if (pair) {
         const int max_cl = ctx->sm_count / 2;
         const int clusters = p.total_tiles < max_cl ? p.total_tiles : max_cl;
-        // f32 residual: three (NB200_GEMM_NP=4: four) residual loads in flight per epilogue warp, paid for with pipeline stages
-        const int np = (e.residual && !e.out_bf16 && p.use_tma) ? ctx->opt.gemm_np : 2;
+        // (more than two staging patches per epilogue warp — deeper residual prefetch at the price of pipeline stages — were measured and
+        // dropped: out-proj 147.6 / 144.1 / 152.9 us and fc2 358 / 394 / 460 us with 2 / 3 / 4 patches, profiles/r2_notes.md)
         if (BN == 128) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<128, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<128, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
-        else if (np == 4) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 4>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 4>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
-        else if (np == 3) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 3>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 3>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
         else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
     } else {
         const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
