@@ -481,6 +481,7 @@ int nb200_create(int ordinal, const nb200_config *cfg, nb200_dtype compute, nb20
         o.gemm_epi_tma = is("NB200_EPI", "direct") ? 0 : 1;
         o.gemm_nofit = env("NB200_GEMM_NOFIT") != nullptr;
         o.gemm_debug = env("NB200_GEMM_DEBUG") ? atoi(env("NB200_GEMM_DEBUG")) : 0;
+        o.gemm_np3 = (env("NB200_GEMM_NP3") && env("NB200_GEMM_NP3")[0] == '1') ? 1 : 0;
         o.gemm_wide = (env("NB200_GEMM_WIDE") && env("NB200_GEMM_WIDE")[0] == '0') ? 0 : 1;
         o.attn_tc = is("NB200_ATTN", "simt") ? 0 : 1;
         o.decode_fused = (env("NB200_DECODE_FUSED") && env("NB200_DECODE_FUSED")[0] == '0') ? 0 : 1;

@@ -84,6 +84,7 @@ struct CtxOptions {
     int gemm_epi_tma = 1;     // NB200_EPI=direct -> 0: thread-per-row stores
     int gemm_nofit = 0;       // NB200_GEMM_NOFIT: keep the pair tile for one window's worth of rows
     int gemm_debug = 0;       // NB200_GEMM_DEBUG: microbenchmark switches of gemm_tc_kernel
+    int gemm_np3 = 0;         // NB200_GEMM_NP3=1: a third staging patch per epilogue warp (4 pipeline stages) for the short-K f32-residual GEMM: out-proj 153.6 -> 156.0 us, off
     int gemm_wide = 1;        // NB200_GEMM_WIDE=0: no single-round wide tiles for one window's worth of rows (gemm_wide_kernel)
     int attn_tc = 1;          // NB200_ATTN=simt -> 0: CUDA-core attention
     int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels

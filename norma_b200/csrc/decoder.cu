@@ -1518,7 +1518,7 @@ __device__ __noinline__ void fs_select_cand_w(const FusedArgs &a, const float *s
 }
 
 __global__ void __launch_bounds__(FS_THREADS, 1)
-decoder_step_fused_kernel(const FusedArgs a) {
+decoder_step_fused_kernel(const __grid_constant__ FusedArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ float red[32];
     __shared__ int red_i[32];

@@ -56,7 +56,7 @@ struct GemmCfg {
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGING = EPI_WARPS * NP * STG_BYTES;
-    static constexpr int BAR_BYTES = 320;
+    static constexpr int BAR_BYTES = 384;
     static constexpr int LN_BYTES = BM * 4;        // 1 / std of the tile's rows (fused LayerNorm consumer)
     static constexpr int BIAS_BYTES = 2 * BN * 4;  // the tile's bias, per accumulator stage
     static constexpr int SMEM_LIMIT = 232448;      // the 227 KB a CTA may opt in to
@@ -403,6 +403,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t rphase = 0;  // bit b: parity of res_bar(ew, b)
         int as = 0;
         uint32_t aphase = 0;
+        // timing build of a launch (NB200_GEMM_DEBUG & 256): clock64 deltas of this warp's phases, summed over its tiles
+        float bias_next = 0.f;
+        static_assert(BN <= 32 * EPI_WARPS, "one bias value per epilogue thread");
+        const bool dbg_on = p.dbg_clk != nullptr;
+        long long d_wait = 0, d_res = 0, d_math = 0, d_st = 0, d_ln = 0, d_tiles = 0, d_chunks = 0, d_t0 = dbg_on ? clock64() : 0;
         int mb, n_idx;
         for (int t = 0; tile_at(t, mb, n_idx); ++t) {
             const int b = mb / p.m_tiles_per_batch, mt = mb - b * p.m_tiles_per_batch;
@@ -413,8 +418,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the tile's bias -> shared memory (all 8 epilogue warps, one L2 round trip in the shadow of the mainloop).  The named barrier also
             // orders the reuse of the buffer two tiles on: every warp has finished tile t - 1, so nobody still reads tile t - 2's values.
             float *bs = bias_smem + as * BN;
-            for (int k = ew * 32 + lane; k < BN; k += 32 * EPI_WARPS) bs[k] = (e.bias && nt0 + k < p.N) ? __ldg(e.bias + nt0 + k) : 0.f;
+            if (t == 0) {
+                for (int k = ew * 32 + lane; k < BN; k += 32 * EPI_WARPS) bs[k] = (e.bias && nt0 + k < p.N) ? __ldg(e.bias + nt0 + k) : 0.f;
+            } else {
+                if (ew * 32 + lane < BN) bs[ew * 32 + lane] = bias_next;  // requested a tile ago (BN <= 256: one value per epilogue thread)
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            {   // the NEXT tile's bias: the load is in flight while this tile's chunks are processed
+                int mb2, n2;
+                bias_next = 0.f;
+                if (tile_at(t + 1, mb2, n2)) {
+                    const int k = n2 * BN + ew * 32 + lane;
+                    if (e.bias && ew * 32 + lane < BN && k < p.N) bias_next = __ldg(e.bias + k);
+                }
+            }
             if (p.use_tma && !no_mem) {
                 if (e.out_bf16) {
                     // ---------- bf16 out: 64-column chunks (128 B rows), no residual ----------
@@ -491,13 +508,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                     }
+                    const long long k0 = dbg_on ? clock64() : 0;
                     ptx::mbar_wait(tfull_bar(as), aphase);
                     ptx::tc_fence_after();
+                    if (dbg_on) { d_wait += clock64() - k0; ++d_tiles; }
 #pragma unroll 1
                     for (int ci = 0; ci < NCI; ++ci) {
                         const int c = 2 * ci + grp;
                         const int n0 = nt0 + c * 32;
                         if (n0 >= p.N) continue;  // warp-uniform
+                        const long long k1 = dbg_on ? clock64() : 0;
                         const int buf = has_res ? ci % NP : (ci & 1);
                         const uint32_t sb = stg + (uint32_t)(buf * STG_BYTES);
                         uint8_t *sbp = stg_ptr + buf * STG_BYTES + lane * 128;
@@ -521,6 +541,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const bool mixed = n0 < e.n_scale && n0 + 32 > e.n_scale;
                         const float cs = (n0 + 32 <= e.n_scale) ? e.scale : 1.0f;
                         ptx::tmem_ld_wait();
+                        const long long k2 = dbg_on ? clock64() : 0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {  // 16-byte group j = columns [4j, 4j+4)
                             const float4 bb = *(const float4 *)(bs + c * 32 + 4 * j);
@@ -547,12 +568,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 acc[4 * j + 2] = __float_as_uint(v[2]); acc[4 * j + 3] = __float_as_uint(v[3]);
                             }
                         }
+                        const long long k3 = dbg_on ? clock64() : 0;
                         ptx::fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
                             ptx::tma_store_3d(&tmOut, sb, n0, r0, b);
                             ptx::bulk_commit();
                         }
+                        const long long k4 = dbg_on ? clock64() : 0;
                         if (ln_out) {
                             if (!(p.debug & 16)) ln_stats_chunk(acc, ln_cnt, ln_mean, ln_m2);
                             if (p.debug & 8) {
@@ -563,6 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 ln_store_bf16_chunk(acc, e.xb_out + (long long)b * e.out_bs + (long long)qr * e.ldo + n0, e.ldo, lane, p.rows_per_batch - qr);
                             }
                         }
+                        if (dbg_on) { const long long k5 = clock64(); d_res += k2 - k1; d_math += k3 - k2; d_st += k4 - k3; d_ln += k5 - k4; ++d_chunks; }
                     }
                     // one partial per (row, n tile, epilogue warp group); the consuming GEMM's statistics warp merges a row's slots
                     if (ln_out && r0 + lane < p.rows_per_batch)
@@ -593,6 +617,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
         if (lane == 0) ptx::bulk_wait_all();  // every bulk store of this thread has been written
+        if (dbg_on && ew == 0 && lane == 0) {
+            long long *o = p.dbg_clk + (size_t)blockIdx.x * 16;
+            o[0] = d_wait; o[1] = d_res; o[2] = d_math; o[3] = d_st; o[4] = d_ln; o[5] = d_tiles; o[6] = d_chunks; o[7] = clock64() - d_t0;
+        }
     }
     ptx::tc_fence_before();
     if (CTA2) ptx::cluster_sync();  // nobody leaves (or frees TMEM) while the peer can still signal into this CTA
@@ -886,6 +914,7 @@ int gemm_tc_init(nb200_ctx *ctx) {
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, false, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128, true, 2>::SMEM_BYTES));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tc_kernel<256, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256, true, 3>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_wide_kernel<160, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<160, 2>::SMEM_BYTES));
     CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_wide_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg<224, 2>::SMEM_BYTES));
     return NB200_OK;
@@ -1032,12 +1061,23 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
     }
     KernelScope ks(ctx, NB200_K_GEMM, (long long)s.N * 100000 + s.K);
     ctx->prof_gemm_flops += 2.0 * s.batch * s.rows_per_batch * (double)s.N * s.K;
+    static thread_local long long *dbg_main = nullptr;  // timing build of a launch only (NB200_GEMM_DEBUG & 256)
+    const bool dbg_main_on = (p.debug & 256) && p.use_tma && !e.out_bf16;
+    if (dbg_main_on) {
+        if (!dbg_main) cudaMalloc(&dbg_main, 148 * 16 * sizeof(long long));
+        cudaMemsetAsync(dbg_main, 0, 148 * 16 * sizeof(long long), ctx->stream);
+        p.dbg_clk = dbg_main;
+    }
     if (pair) {
         const int max_cl = ctx->sm_count / 2;
         const int clusters = p.total_tiles < max_cl ? p.total_tiles : max_cl;
         // (more than two staging patches per epilogue warp — deeper residual prefetch at the price of pipeline stages — were measured and
         // dropped: out-proj 147.6 / 144.1 / 152.9 us and fc2 358 / 394 / 460 us with 2 / 3 / 4 patches, profiles/r2_notes.md)
+        // f32 residual with a short K (out-proj): the epilogue is the critical path and every chunk waits for its residual tile; a third staging
+        // patch per warp keeps one more residual load in flight, paid for with a pipeline stage (NB200_GEMM_NP3=0 disables)
+        const bool np3 = ctx->opt.gemm_np3 && e.residual && !e.out_bf16 && p.use_tma && s.K <= 2048 && BN == 256;
         if (BN == 128) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<128, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<128, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
+        else if (np3) CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 3>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 3>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
         else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<256, true, 2>, dim3(2 * clusters), dim3(GEMM_THREADS), GemmCfg<256, true, 2>::SMEM_BYTES, 2, tmA, tmB, tmOut, tmRes, p));
     } else {
         const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
@@ -1045,5 +1085,17 @@ int launch_gemm_bf16(nb200_ctx *ctx, const bf16 *A, const bf16 *W, const GemmSha
         else CUDA_TRY(ctx, launch_chain(ctx, 1, gemm_tc_kernel<128, false, 2>, dim3(grid), dim3(GEMM_THREADS), GemmCfg<128, false, 2>::SMEM_BYTES, 1, tmA, tmB, tmOut, tmRes, p));
     }
     CUDA_TRY(ctx, cudaGetLastError());
+    if (dbg_main_on) {  // where an epilogue warp's cycles go (warp 4 of every CTA, averaged; stderr)
+        std::vector<long long> h(148 * 16);
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(h.data(), dbg_main, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 148; ++c)
+            for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)c * 16 + i];
+        if (a[5] > 0 && a[6] > 0)
+            fprintf(stderr, "[gemm_tc f32 epilogue N=%d K=%d ln=%d] warp 4, clk: accumulator wait %.0f per tile | per 32-column chunk: tcgen05.ld + residual wait %.0f | math + "
+                            "st.shared %.0f | fence + store issue %.0f | statistics + bf16 copy %.0f | %.1f chunks per tile, whole kernel %.0f clk for %.1f tiles per CTA\n",
+                    s.N, s.K, e.stats_out != nullptr, a[0] / a[5], a[1] / a[6], a[2] / a[6], a[3] / a[6], a[4] / a[6], a[6] / a[5], a[7] / 148.0, a[5] / 148.0);
+    }
     return NB200_OK;
 }
