@@ -581,8 +581,9 @@ def main():
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         # `traffic` is NOT measured by this run: it is the ALGORITHMIC HBM bytes per launch computed from the shape (operands once + f32 residual in /
         # out, mean of a layer's four GEMMs).  The measured DRAM bytes of the same launches are in the ncu capture named below.
-        "traffic": wl.gemm_bytes(c, B, es), "traffic_kind": "algorithmic bytes per launch computed from the shape (not measured here)",
-        "traffic_measured_in": "profiles/r1e_gemm_full_summary.md (ncu --set full, B = 25: 346 / 436 / 444 / 850 MB for qkv / out / fc1 / fc2, mean 519 MB)",
+        "traffic": wl.gemm_bytes(c, B, es, ln_folded=(args.compute == "bf16" and os.environ.get("NB200_LN_FUSED", "1") != "0")),
+        "traffic_kind": "algorithmic bytes per launch computed from the shape, LayerNorm folded (not measured here)",
+        "traffic_measured_in": "profiles/r2h_gemm_full_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
         "peak_source": peak_src,
         "flops_per_launch": gflops / gemm_launches, "avg_launch_ms": gemm_ms / gemm_launches, "launches": gemm_launches,
         "profiled_ms_per_step": ms_prof / args.steps,

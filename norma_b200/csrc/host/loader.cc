@@ -308,15 +308,18 @@ bool Safetensors::open(const std::string &path, std::string *err) {
         for (auto &d : sh->arr) {
             if (d.kind != nb200json::Value::Number || !d.is_int || d.inum < 0) { *err = "safetensors: bad shape for '" + kv.first + "'"; return false; }
             e.shape.push_back(d.inum);
-            count *= (size_t)d.inum;
+            // overflow-checked: a crafted shape such as [2^62, 4] must not wrap round to a count that matches an empty byte range
+            if (__builtin_mul_overflow(count, (size_t)d.inum, &count)) { *err = "safetensors: shape of '" + kv.first + "' overflows"; return false; }
         }
+        size_t want_bytes = 0;
+        if (__builtin_mul_overflow(count, esz, &want_bytes)) { *err = "safetensors: size of '" + kv.first + "' overflows"; return false; }
         if (off->arr[0].kind != nb200json::Value::Number || off->arr[1].kind != nb200json::Value::Number || off->arr[0].inum < 0 || off->arr[1].inum < off->arr[0].inum) {
             *err = "safetensors: bad data_offsets for '" + kv.first + "'";
             return false;
         }
         e.begin = (size_t)off->arr[0].inum;
         e.end = (size_t)off->arr[1].inum;
-        if (e.end > data_len || e.end - e.begin != count * esz) {  // safetensors' TensorInvalidInfo / MetadataIncompleteBuffer checks
+        if (e.end > data_len || e.end - e.begin != want_bytes) {  // safetensors' TensorInvalidInfo / MetadataIncompleteBuffer checks
             *err = "safetensors: tensor '" + kv.first + "' byte range does not match its dtype and shape";
             return false;
         }
@@ -415,7 +418,7 @@ bool Gguf::open(const std::string &path, std::string *err) {
             const uint64_t dk = c.get<uint64_t>();
             if (dk == 0 || dk > (1ull << 40)) { *err = "gguf: bad dimension in '" + e.name + "'"; return false; }
             dims[k] = (int64_t)dk;
-            e.numel *= (size_t)dk;
+            if (__builtin_mul_overflow(e.numel, (size_t)dk, &e.numel)) { *err = "gguf: shape of '" + e.name + "' overflows"; return false; }
         }
         e.shape.assign(dims.rbegin(), dims.rend());  // innermost-first -> row-major
         e.type = c.get<uint32_t>();
@@ -426,13 +429,15 @@ bool Gguf::open(const std::string &path, std::string *err) {
     data_off_ = ((size_t)(c.p - base_) + alignment - 1) / alignment * alignment;
     for (auto &e : entries_) {
         size_t bytes;
+        if (e.numel > size_) { *err = "gguf: tensor '" + e.name + "' has more elements than the file has bytes"; return false; }  // also bounds the products below
         if (e.type == 0) bytes = e.numel * 4;
         else if (e.type == 1) bytes = e.numel * 2;
         else if (e.type == 8) {
             if (e.shape.back() % 32) { *err = "gguf: Q8_0 tensor '" + e.name + "' has a row length that is not a multiple of 32"; return false; }
             bytes = e.numel / 32 * 34;
         } else { *err = "gguf: tensor '" + e.name + "' has unsupported type " + std::to_string(e.type) + " (F32, F16 and Q8_0 are read)"; return false; }
-        if (data_off_ + e.offset + bytes > size_) { *err = "gguf: tensor '" + e.name + "' runs past the end of the file"; return false; }
+        // step by step against what is left of the file: a large u64 offset must not wrap the sum
+        if (data_off_ > size_ || e.offset > size_ - data_off_ || bytes > size_ - data_off_ - e.offset) { *err = "gguf: tensor '" + e.name + "' runs past the end of the file"; return false; }
     }
     return true;
 }

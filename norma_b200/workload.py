@@ -56,13 +56,17 @@ def layernorm_bytes_per_row(d: int, out_bytes: int = 2) -> float:
     return (4.0 + out_bytes) * d
 
 
-def gemm_bytes(c: Dict[str, int], B: int, es: int = 2) -> float:
-    """Algorithmic HBM bytes of one layer's four GEMMs at B windows (operands once, f32 residual in and out), mean per launch."""
+def gemm_bytes(c: Dict[str, int], B: int, es: int = 2, ln_folded: bool = True) -> float:
+    """Algorithmic HBM bytes of one layer's four GEMMs at B windows (operands once, f32 residual in and out), mean per launch.
+    `ln_folded` (the bf16 build): out-proj and fc2 also write the bf16 copy of the residual rows and 2 x d / 256 float2 statistics slots per row,
+    the QKV / fc1 GEMMs read the slots (the 2 x (4 + 2) d bytes per row of the two LayerNorm kernels they replace are gone from the step)."""
     d, M = c["d_model"], B * T_ENC
-    qkv = es * (M * d + 3 * d * d + M * 3 * d)
-    out = es * (M * d + d * d) + 8.0 * M * d
-    fc1 = es * (M * d + 4 * d * d + M * 4 * d)
-    fc2 = es * (M * 4 * d + 4 * d * d) + 8.0 * M * d
+    slots = 8.0 * 2 * max(1, d // 256) * M if ln_folded else 0.0  # 256-wide pair tiles x 2 epilogue warp groups
+    copy = 2.0 * M * d if ln_folded else 0.0
+    qkv = es * (M * d + 3 * d * d + M * 3 * d) + slots
+    out = es * (M * d + d * d) + 8.0 * M * d + copy + slots
+    fc1 = es * (M * d + 4 * d * d + M * 4 * d) + slots
+    fc2 = es * (M * 4 * d + 4 * d * d) + 8.0 * M * d + copy + slots
     return (qkv + out + fc1 + fc2) / 4.0
 
 

@@ -229,7 +229,7 @@ def _raw_safetensors(path, header: dict, data: bytes, hlen=None):
         f.write(data)
 
 
-@pytest.mark.parametrize("case", ["short", "hlen", "json", "range", "size", "dtype", "offsets"])
+@pytest.mark.parametrize("case", ["short", "hlen", "json", "range", "size", "dtype", "offsets", "overflow"])
 def test_safetensors_malformed_files_are_parse_errors(lib, tmp_path, case):
     p = str(tmp_path / "bad.safetensors")
     ok = {"t": {"dtype": "F32", "shape": [2, 2], "data_offsets": [0, 16]}}
@@ -247,6 +247,8 @@ def test_safetensors_malformed_files_are_parse_errors(lib, tmp_path, case):
         _raw_safetensors(p, {"t": {"dtype": "I64", "shape": [2], "data_offsets": [0, 16]}}, b"\0" * 16)
     elif case == "offsets":
         _raw_safetensors(p, {"t": {"dtype": "F32", "shape": [2, 2], "data_offsets": [16, 0]}}, b"\0" * 16)
+    elif case == "overflow":  # 2^62 x 4 elements x 4 bytes wraps round to 0 bytes: must not pass as an empty tensor
+        _raw_safetensors(p, {"t": {"dtype": "F32", "shape": [1 << 62, 4], "data_offsets": [0, 0]}}, b"\0" * 16)
     with pytest.raises(ffi.Nb200Error) as e:
         ffi.safetensors_read(p, "t")
     assert e.value.status == 8
@@ -293,7 +295,7 @@ def test_gguf_v2_and_alignment(lib, tmp_path):
             assert np.array_equal(ffi.gguf_read(p, k)[0], deq[k])
 
 
-@pytest.mark.parametrize("case", ["magic", "version", "truncated", "type", "row", "short"])
+@pytest.mark.parametrize("case", ["magic", "version", "truncated", "type", "row", "short", "offset_wrap", "numel_wrap"])
 def test_gguf_malformed_files_are_parse_errors(lib, tmp_path, case):
     p = str(tmp_path / "bad.gguf")
     synth.write_gguf(p, {"t": np.ones((2, 32), np.float32)})
@@ -314,6 +316,14 @@ def test_gguf_malformed_files_are_parse_errors(lib, tmp_path, case):
         raw[j:j + 8] = struct.pack("<Q", 31)                    # innermost dimension no longer a multiple of 32
     elif case == "short":
         raw = raw[:10]
+    elif case == "offset_wrap":  # data offset close to 2^64: data_off + offset + bytes wraps round
+        i = raw.index(b"\x01\x00\x00\x00\x00\x00\x00\x00t")
+        j = i + 9 + 4 + 16 + 4                                  # name, rank, two dims, type
+        raw[j:j + 8] = struct.pack("<Q", (1 << 64) - 64)
+    elif case == "numel_wrap":  # 2^40 x 2^40 elements
+        i = raw.index(b"\x01\x00\x00\x00\x00\x00\x00\x00t")
+        j = i + 9 + 4
+        raw[j:j + 16] = struct.pack("<QQ", 1 << 40, 1 << 40)
     open(p, "wb").write(bytes(raw))
     with pytest.raises(ffi.Nb200Error) as e:
         ffi.gguf_read(p, "t")
