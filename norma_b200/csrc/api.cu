@@ -1363,9 +1363,12 @@ int nb200_flush_l2(nb200_ctx *ctx) {
 }
 
 int nb200_test_gemm(nb200_ctx *ctx, const void *a, const void *w, const float *bias, int M, int N, int K, int act_gelu, float *c_out) {
+    // act_gelu: bit 0 = tanh-GELU; bit 1 (bf16 contexts) = take the bf16-output epilogue (the QKV / fc1 path, incl. the single-round wide
+    // tiles at M <= 1536 and N > 1536) and widen the result to f32 on the way out
     NB_TRY(check_ready(ctx, false, false));
     if (!a || !w || !c_out || M < 1 || N < 1 || K < 1) return nb200_fail(ctx, NB200_INVALID_ARG, "test_gemm: bad argument");
     const size_t es = dtype_size(ctx->compute);
+    const bool out16 = (act_gelu & 2) && ctx->compute == NB200_BF16;
     void *dA = nullptr, *dW = nullptr;
     float *dB = nullptr, *dC = nullptr;
     int st = [&]() -> int {
@@ -1381,9 +1384,16 @@ int nb200_test_gemm(nb200_ctx *ctx, const void *a, const void *w, const float *b
         }
         GemmShape s{M, 1, N, K, K, (long long)M * K};
         Epilogue e{};
-        e.bias = dB; e.act = act_gelu; e.out = dC; e.ldo = N; e.out_bf16 = 0;
+        e.bias = dB; e.act = act_gelu & 1; e.out = dC; e.ldo = N; e.out_bf16 = out16 ? 1 : 0;
         if (ctx->compute == NB200_BF16) NB_TRY(launch_gemm_bf16(ctx, (const bf16 *)dA, (const bf16 *)dW, s, e));
         else NB_TRY(launch_gemm_f32(ctx, (const float *)dA, (const float *)dW, s, e));
+        if (out16) {
+            std::vector<uint16_t> h((size_t)M * N);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), dC, h.size() * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (size_t i = 0; i < h.size(); ++i) c_out[i] = bf16_bits_to_float(h[i]);
+            return NB200_OK;
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(c_out, dC, (size_t)M * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return NB200_OK;

@@ -548,7 +548,7 @@ class Context:
         self._ck(self.lib.nb200_flush_l2(self.h))
 
     # -- kernel self-tests -----------------------------------------------------------------------------------
-    def test_gemm(self, a: np.ndarray, w: np.ndarray, bias: Optional[np.ndarray] = None, gelu=False) -> np.ndarray:
+    def test_gemm(self, a: np.ndarray, w: np.ndarray, bias: Optional[np.ndarray] = None, gelu=False, out_bf16=False) -> np.ndarray:
         M, K = a.shape
         N = w.shape[0]
         if self.compute == "bf16":
@@ -557,7 +557,7 @@ class Context:
             a_, w_ = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(w, np.float32)
         b_ = None if bias is None else np.ascontiguousarray(bias, np.float32)
         out = np.empty((M, N), np.float32)
-        self._ck(self.lib.nb200_test_gemm(self.h, a_.ctypes.data_as(C.c_void_p), w_.ctypes.data_as(C.c_void_p), _f32p(b_), M, N, K, int(gelu), _f32p(out)))
+        self._ck(self.lib.nb200_test_gemm(self.h, a_.ctypes.data_as(C.c_void_p), w_.ctypes.data_as(C.c_void_p), _f32p(b_), M, N, K, int(gelu) | (2 if out_bf16 else 0), _f32p(out)))
         return out
 
     def test_gemm_perf(self, M: int, N: int, K: int, epi_kind: int, iters: int = 20) -> float:

@@ -8,7 +8,7 @@ st = synth.special_tokens(c["vocab_size"])
 d, V, L = c["d_model"], c["vocab_size"], c["decoder_layers"]
 bytes_tok = 2.0 * (L * 14 * d * d + V * d)
 for B in [int(x) for x in os.environ.get("BS", "1,8").split(",")]:
-    ctx = ffi.Context(c, compute="bf16", max_batch=B)
+    ctx = ffi.Context(c, compute="bf16", max_batch=max(B, int(os.environ.get("MAXB", "0"))))
     ctx.set_mel_filters(filters.mel_filters(c["num_mel_bins"])); ctx.load_weights(w); ctx.set_tokens(**st)
     pcm = np.stack([synth.synth_pcm_window(i) for i in range(B)])
     ctx.transcode_batch(pcm, want_output=False)

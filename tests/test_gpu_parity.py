@@ -118,6 +118,28 @@ def test_tcgen05_gemm_vs_fp64(lib, M, N, K):
     ctx.close()
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(1500, 3840, 1280, False), (1500, 5120, 1280, True), (1333, 3840, 256, False), (1500, 3072, 1024, True),
+                                        (3000, 3840, 1280, False), (700, 256, 128, True)])
+def test_tcgen05_gemm_bf16_output_vs_fp64(lib, M, N, K, gelu):
+    """The bf16-output epilogue (bias, tanh-GELU) against fp64.  The first four shapes take gemm_wide_kernel (one window's worth of rows,
+    N > 1536): 256 x 320 tiles at N = 3840 / 3072 (the last n tile partial at 3072), 256 x 448 at N = 5120 (last tile 192 of 448 columns),
+    ragged rows, a short K (4 k-blocks in a 6-stage ring); the last two the persistent 256 x 256 / 128 x 128 tiles."""
+    rng = np.random.default_rng(M + N + K)
+    ctx = ffi.Context(synth.model_config("test-micro"), compute="bf16", max_batch=1)
+    a = ffi.bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = ffi.bf16_round((rng.standard_normal((N, K)) * 0.05).astype(np.float32))
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = a.astype(np.float64) @ w.astype(np.float64).T + bias
+    if gelu:
+        ref = 0.5 * ref * (1.0 + np.tanh(0.7978845608028654 * ref * (1.0 + 0.044715 * ref * ref)))
+    got = ctx.test_gemm(a, w, bias, gelu=gelu, out_bf16=True)
+    assert not np.isnan(got).any()
+    # one bf16 rounding of the result (2^-9 relative) on top of the fp32 accumulation and tanh.approx
+    assert np.abs(got - ref).max() <= 2 ** -8 * max(1.0, np.abs(ref).max()) * 0.5 + 2e-5 * np.sqrt(K) + (2e-3 if gelu else 0.0)
+    assert np.abs(got - ref).mean() <= 2e-3
+    ctx.close()
+
+
 @pytest.mark.parametrize("compute,tol", [("f32", 5e-6), ("bf16", 8e-3)])
 @pytest.mark.parametrize("B,T,H", [(1, 64, 2), (2, 200, 2), (1, 1500, 3), (2, 1, 2)])
 def test_attention_vs_fp64(lib, compute, tol, B, T, H):
