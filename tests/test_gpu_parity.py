@@ -134,9 +134,12 @@ def test_tcgen05_gemm_bf16_output_vs_fp64(lib, M, N, K, gelu):
         ref = 0.5 * ref * (1.0 + np.tanh(0.7978845608028654 * ref * (1.0 + 0.044715 * ref * ref)))
     got = ctx.test_gemm(a, w, bias, gelu=gelu, out_bf16=True)
     assert not np.isnan(got).any()
-    # one bf16 rounding of the result (2^-9 relative) on top of the fp32 accumulation and tanh.approx
-    assert np.abs(got - ref).max() <= 2 ** -8 * max(1.0, np.abs(ref).max()) * 0.5 + 2e-5 * np.sqrt(K) + (2e-3 if gelu else 0.0)
-    assert np.abs(got - ref).mean() <= 2e-3
+    # one bf16 rounding of the result (half an ulp = 2^-8 relative at worst) on top of the fp32 accumulation and tanh.approx
+    err = np.abs(got - ref)
+    bound = 2.0 ** -8 * np.maximum(1.0, np.abs(ref)) + 2e-5 * np.sqrt(K) + (2e-3 if gelu else 0.0)
+    worst = np.unravel_index(np.argmax(err - bound), err.shape)
+    assert (err <= bound).all(), (worst, float(got[worst]), float(ref[worst]), float(err[worst]))
+    assert err.mean() <= 4e-3
     ctx.close()
 
 
