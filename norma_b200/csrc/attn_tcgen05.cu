@@ -59,7 +59,7 @@ __device__ __forceinline__ void pin16(const uint32_t *r) {
 #endif
 template <bool MASK>
 __device__ __forceinline__ void softmax_tile(uint32_t tSj, uint32_t tO, uint32_t s_full, uint32_t s_par, uint32_t p_full, uint32_t o_done, uint32_t o_par_prev,
-                                              int lane, bool first, int valid, float &m, float &l, long long *tm = nullptr) {
+                                              int lane, bool first, bool have_prev, int valid, float &m, float &l, long long *tm = nullptr) {
 #ifdef NB200_ATTN_TIMING
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
 #endif
@@ -106,11 +106,19 @@ __device__ __forceinline__ void softmax_tile(uint32_t tSj, uint32_t tO, uint32_t
     pin16(sv); pin16(sv + 16);
 #endif
     AT_CLK(c3);
+    // P(j-1).V must have RETIRED before P(j) is stored.  Nothing in the dataflow asks for it (P(j) goes to its own score buffer, and only a
+    // rescale touches O), but with two CTAs per SM a tcgen05.st issued while the previous TS-form MMA is still reading ITS A operand from
+    // tensor memory corrupted single rows of that product: the last windows of a 25-window batch differed from run to run by up to 0.3 in a
+    // few hundred rows (scripts/gpu_attn_determinism.py: 6 of 6 repetitions; none with this wait; the same wait in front of the
+    // tcgen05.ld costs 11 % instead of 3 %, issuing S one tile later 30 %).  The barrier has normally completed long before: P(j-1).V is
+    // issued when the softmax of tile j starts.  `have_prev`: false only for the CTA's very first tile.
+    if (have_prev) {
+        ptx::mbar_wait(o_done, o_par_prev);
+        ptx::tc_fence_after();
+    }
     ptx::tmem_st_32x32b_x32(tSj, sv);  // P(j): 64 bf16 = 32 packed columns, over the first half of S(j)
     AT_CLK(c4);
-    if (!first && moved) {
-        ptx::mbar_wait(o_done, o_par_prev);  // only a rescale has to see P(j-1).V(j-1) retired
-        ptx::tc_fence_after();
+    if (!first && moved) {  // (P(j-1).V has retired, see above)
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             uint32_t ov[32];
@@ -289,12 +297,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < nkv - 1; ++j, ++g) {
                 const int sb = g % NS;
                 softmax_tile<false>(tmem_base + lane_off + sb * 64, tO + lane_off, bar + L::B_SF + 8 * sb, (uint32_t)((g / NS) & 1), bar + L::B_PF + 8 * sb,
-                                     bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, j == 0, 64, m, l, tm);
+                                     bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, j == 0, g > 0, 64, m, l, tm);
             }
             {
                 const int sb = g % NS;
                 softmax_tile<true>(tmem_base + lane_off + sb * 64, tO + lane_off, bar + L::B_SF + 8 * sb, (uint32_t)((g / NS) & 1), bar + L::B_PF + 8 * sb,
-                                    bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, nkv == 1, T - (nkv - 1) * BN, m, l, tm);
+                                    bar + L::B_OD, (uint32_t)((g - 1) & 1), lane, nkv == 1, g > 0, T - (nkv - 1) * BN, m, l, tm);
                 ++g;
             }
             AT_CLK(e0);
@@ -362,7 +370,8 @@ int launch_attention_tc(nb200_ctx *ctx, const bf16 *qkv, bf16 *out, int B, int T
     NB_TRY(tmap_encode_bf16(ctx, &tkv, qkv, 3, dims, str, box_kv));
     KernelScope ks(ctx, NB200_K_ATTN);
     const int n_items = ceil_div(T, AT_BM) * n_heads * B;   // (window, head, query tile), query tile fastest: CTAs that run together share K / V in L2
-    const int ctas = std::min(n_items, 2 * ctx->sm_count);  // persistent: two resident CTAs per SM
+    int ctas = std::min(n_items, 2 * ctx->sm_count);  // persistent: two resident CTAs per SM
+    if (const char *e = getenv("NB200_ATTN_CTAS")) ctas = std::max(1, std::min(n_items, atoi(e)));  // scripts/gpu_attn_determinism.py: grid size
     unsigned long long *dbg = nullptr;
 #ifdef NB200_ATTN_TIMING
     static unsigned long long *dbg_buf = nullptr;

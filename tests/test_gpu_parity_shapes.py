@@ -282,3 +282,19 @@ def test_layernorm_fold_matches_standalone_layernorm_and_oracle(lib, monkeypatch
     assert r1 <= 1e-2 and r0 <= 1e-2
     assert r1 <= 1.5 * r0 + 1e-3  # folding must not cost accuracy
     assert got["0n"] - got["1n"] == 2 * c["encoder_layers"]  # every LayerNorm but ln_post is gone
+
+
+# ------------------------------------------------------------------------------------------------ (f) repeatability at the bench batch
+def test_encoder_is_bitwise_repeatable_at_25_windows(lib):
+    """The bench's batch (25 windows, d_model 1280, 20 heads; 4 layers to keep it short) three times through nb200_transcode_batch: bit-equal.
+    At this batch every persistent attention CTA walks 20 items; before the round-2 fix windows 22..24 differed from run to run."""
+    c = dict(synth.model_config("distil-large-v3"), encoder_layers=4)
+    ctx = ffi.Context(c, compute="bf16", max_batch=25)
+    ctx.set_mel_filters(filters.mel_filters(128))
+    ctx.load_weights(synth.synth_weights(c, seed=1, decoder=False))
+    pcm = np.stack([synth.synth_pcm_window(i) for i in range(25)])
+    ref = ctx.transcode_batch(pcm).copy()
+    assert not np.isnan(ref).any()
+    for _ in range(2):
+        assert np.array_equal(ctx.transcode_batch(pcm), ref)
+    ctx.close()
