@@ -43,6 +43,11 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 #ifdef NB200_ATTN_TIMING
 // Empty asm that consumes 16 registers: everything they depend on is computed before the next asm volatile as far as nvcc is
 // concerned (ptxas may still sink it).  Only the timing build uses it, to keep the clock64 brackets honest.
@@ -91,15 +96,22 @@ __device__ __forceinline__ void softmax_tile(uint32_t tSj, uint32_t tO, uint32_t
     const bool moved = __any_sync(0xffffffffu, (m_cand - m) * LOG2E > RESCALE_LOG2);
     const float m_new = moved ? m_cand : m;
     const float mb = m_new * LOG2E;
-    float rs0 = 0.f, rs1 = 0.f;
+    // scale / subtract and the two row-sum chains as packed f32x2 operations (fma.rn.f32x2 / add.rn.f32x2: one issue slot per PAIR, the
+    // same roundings as the scalar forms): the XU pipe is the bound, but the softmax stream alone reaches only 78 % of it and every issue
+    // slot taken out of the loop helps the two warps of a scheduler interleave (scripts/probes/mufu_probe2.cu: V0 1 310 -> V3 1 195 clk per tile)
+    const uint64_t c2 = pack2(LOG2E, LOG2E), nmb2 = pack2(-mb, -mb);
+    uint64_t rs2 = pack2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), LOG2E, -mb)), p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), LOG2E, -mb));
-        rs0 += p0;
-        rs1 += p1;
+        float a, b;
+        unpack2(fma2(pack2(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), c2, nmb2), a, b);
+        const float p0 = ex2(a), p1 = ex2(b);
+        rs2 = add2(rs2, pack2(p0, p1));
         __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
         sv[i] = *(uint32_t *)&t;
     }
+    float rs0, rs1;
+    unpack2(rs2, rs0, rs1);
     const float alpha = ex2((m - m_new) * LOG2E);
     l = l * alpha + (rs0 + rs1);
 #ifdef NB200_ATTN_TIMING
