@@ -253,14 +253,19 @@ def test_streaming_bit_identity_distil_large_v3_shape(lib):
 
 
 # ------------------------------------------------------------------------------------------------ (e) LayerNorm folded into the GEMMs
-@pytest.mark.parametrize("name,shift", [("tiny.en", 0.0), ("base.en", 0.0), ("base.en", 1.5)])
+@pytest.mark.parametrize("name,shift", [("tiny.en", 0.0), ("base.en", 0.0), ("base.en", 1.5), ("base.en", -40.0)])
 def test_layernorm_fold_matches_standalone_layernorm_and_oracle(lib, monkeypatch, name, shift):
     """bf16 encoder with the LayerNorms folded into the QKV / fc1 GEMMs (default) against (a) the same context with standalone LayerNorm
     kernels (NB200_LN_FUSED=0) and (b) the oracle: both within the north-star 1e-2.  `shift` moves every residual-stream row off zero mean
-    (conv2 bias + shift: row mean ~ shift against a row std of ~1), the case where x . W'^T - mean . (W' . 1) has something to cancel."""
+    (conv2 bias + shift: row mean ~ shift against a row std of ~1), the case where the centring inside the weight has something to cancel; a
+    negative `shift` plants four outlier channels of that magnitude instead (row std ~ 3.5, a few values 40x the rest)."""
     c = synth.model_config(name)
     w = synth.synth_weights(c, seed=2, decoder=False)
-    w["model.encoder.conv2.bias"] = w["model.encoder.conv2.bias"] + shift
+    if shift < 0:  # "massive activations": four channels of the residual stream sit at |shift| in every row (as trained Whisper checkpoints have)
+        w["model.encoder.conv2.bias"] = w["model.encoder.conv2.bias"].clone()
+        w["model.encoder.conv2.bias"][[3, 77, 200, 311]] += -shift
+    else:
+        w["model.encoder.conv2.bias"] = w["model.encoder.conv2.bias"] + shift
     f = filters.mel_filters(c["num_mel_bins"])
     pcm = np.stack([synth.synth_pcm("gauss", 5), synth.synth_pcm("uniform", 6), synth.synth_pcm("bursts", 7)])
     mel = np.stack([mel_c.pcm_to_mel(p, f)[:, :3000] for p in pcm])
