@@ -13,8 +13,9 @@
 //               probabilities go straight back into the TMEM columns the scores came from (tcgen05.st): P never touches shared
 //               memory.  The running maximum only moves when a row outgrows it by 2^8 (lazy rescale), so the O accumulator is
 //               rarely touched; final O / l -> bf16 -> global.
-// Nothing in the softmax loop waits for P.V: the scores of the next two tiles are already in the other S buffers, and the tensor
-// core computes the first scores of the next item while the softmax warps write this item's output.
+// The softmax loop does not wait for the current tile's P.V: the scores of the next two tiles are already in the other S buffers, and the
+// tensor core computes the first scores of the next item while the softmax warps write this item's output.  It does wait, just before it
+// stores P(j), for P(j-1).V to have retired (see softmax_tile: a correctness requirement found in round 2, normally satisfied long before).
 //
 // How it got here, with the measurements (profiles/r1d_attention_notes.md): the bound for head_dim 64 on B200 is the XU pipe
 // (16 ex2 / clk / SM: 1024 clk per 128 x 128 tile, measured by scripts/probes/mufu_probe.cu), not the tensor core (512 clk); the
