@@ -90,9 +90,10 @@ struct CtxOptions {
     int decode_fused = 1;     // NB200_DECODE_FUSED=0 -> per-operation decode kernels
     int decode_graph = 1;     // NB200_DECODE_NOGRAPH -> 0
     int encoder_graph = 1;    // NB200_ENCODER_NOGRAPH -> 0: launch the encoder kernel by kernel
-    int pdl = 0;              // NB200_PDL: bit mask of the kernels launched with programmatic dependent launch (1 GEMM, 2 attention, 4 LayerNorm);
-                              // off: measured 3.702 vs 3.719 ms per window (kernels of the chain own their SM, only prologues overlap) and,
-                              // with the folded LayerNorm, the streaming path lost its bit-identity with the one-shot path (profiles/r2_notes.md)
+    int pdl = 7;              // NB200_PDL: bit mask of the kernels launched with programmatic dependent launch (1 GEMM, 2 attention, 4 LayerNorm;
+                              // 0 = off).  Every kernel of the chain owns its SM's shared memory, so only the ~1 us prologue (barrier init, TMEM
+                              // allocation, tensor-map prefetch) overlaps the previous kernel's tail: 3.19 -> 3.12 ms per window, nothing at 25
+                              // windows.  (It looked unstable earlier in round 2; that was the attention race, profiles/r2_notes.md sections 1, 3.)
     int ln_fused = 1;         // NB200_LN_FUSED=0 -> standalone LayerNorm kernels in the encoder
     int prof_dump = 0;        // NB200_PROF_DUMP
 };
